@@ -1,0 +1,152 @@
+"""Oracle (test infrastructure): restated diffusers==0.26.3 schedulers + sinusoid.
+
+Third-party algorithm restated from its published semantics; the reference
+pins the version at requirements.txt:3 and calls it at
+  * DDIMScheduler: pipeline.py:105,307; ddim/pnp_pipeline.py:133,192,262-267;
+    diffusion/ip_adapter/custom_pipelines.py:250,334,357
+  * DDPMScheduler: prior/model.py:134,585,648
+  * get_timestep_embedding: prior/model.py:565-568,613-614
+Scheduler config = the SDXL-base hub ``scheduler_config.json``.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+SDXL_SCHEDULER_CONFIG = dict(
+    num_train_timesteps=1000,
+    beta_start=0.00085,
+    beta_end=0.012,
+    beta_schedule="scaled_linear",
+    prediction_type="epsilon",
+    steps_offset=1,
+    timestep_spacing="leading",
+    clip_sample=False,
+    set_alpha_to_one=False,
+)
+
+
+def get_timestep_embedding(timesteps, embedding_dim, flip_sin_to_cos=False,
+                           downscale_freq_shift=1, scale=1, max_period=10000):
+    """diffusers.models.embeddings.get_timestep_embedding."""
+    assert timesteps.ndim == 1
+    half = embedding_dim // 2
+    exponent = -math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=timesteps.device)
+    exponent = exponent / (half - downscale_freq_shift)
+    emb = torch.exp(exponent)
+    emb = timesteps[:, None].float() * emb[None, :]
+    emb = scale * emb
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    if flip_sin_to_cos:
+        emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+    if embedding_dim % 2 == 1:
+        emb = torch.nn.functional.pad(emb, (0, 1, 0, 0))
+    return emb
+
+
+def _alphas_cumprod(cfg):
+    assert cfg["beta_schedule"] == "scaled_linear"
+    betas = torch.linspace(cfg["beta_start"] ** 0.5, cfg["beta_end"] ** 0.5,
+                           cfg["num_train_timesteps"], dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def _leading_timesteps(cfg, n):
+    ratio = cfg["num_train_timesteps"] // n
+    ts = (np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64)
+    return ts + cfg["steps_offset"]
+
+
+class _Base:
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, **overrides):
+        cfg = dict(SDXL_SCHEDULER_CONFIG)
+        cfg.update(overrides)
+        self.config = SimpleNamespace(**cfg)
+        self._cfg = cfg
+        self.alphas_cumprod = _alphas_cumprod(cfg)
+        self.one = torch.tensor(1.0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if cfg["set_alpha_to_one"] else self.alphas_cumprod[0]
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, cfg["num_train_timesteps"])[::-1].copy().astype(np.int64))
+
+    @classmethod
+    def from_config(cls, config):
+        if not isinstance(config, dict):
+            config = {k: v for k, v in vars(config).items() if k in SDXL_SCHEDULER_CONFIG}
+        return cls(**{k: v for k, v in config.items() if k in SDXL_SCHEDULER_CONFIG})
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        self.num_inference_steps = num_inference_steps
+        self.timesteps = torch.from_numpy(_leading_timesteps(self._cfg, num_inference_steps)).to(device)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+
+class DDIMSchedulerOracle(_Base):
+    """DDIMScheduler.step, eta / variance-noise supported."""
+
+    def step(self, model_output, timestep, sample, eta=0.0, generator=None,
+             variance_noise=None, return_dict=False):
+        t = int(timestep)
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        variance = ((1 - a_p) / (1 - a_t)) * (1 - a_t / a_p)
+        std = eta * variance ** 0.5
+        direction = (1 - a_p - std ** 2) ** 0.5 * model_output
+        prev = a_p ** 0.5 * x0 + direction
+        if eta > 0:
+            if variance_noise is None:
+                variance_noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+            prev = prev + std * variance_noise
+        return (prev,)
+
+
+class DDPMSchedulerOracle(_Base):
+    """DDPMScheduler.step with variance_type="fixed_small" (SURVEY.md A.5)."""
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=False):
+        t = int(timestep)
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        b_t = 1 - a_t
+        b_p = 1 - a_p
+        cur_a = a_t / a_p
+        cur_b = 1 - cur_a
+        x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        c0 = (a_p ** 0.5 * cur_b) / b_t
+        cx = cur_a ** 0.5 * b_p / b_t
+        prev = c0 * x0 + cx * sample
+        if t > 0:
+            # randn_tensor(shape, generator=generator, device, dtype): global RNG when generator is None
+            noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+            var = torch.clamp((1 - a_p) / (1 - a_t) * cur_b, min=1e-20)
+            prev = prev + (var ** 0.5) * noise
+        return (prev,)
+
+
+def backward_ddim(x_tm1, alpha_t, alpha_tm1, eps_xt):
+    """Restatement of ``_backward_ddim`` (ddim/pnp_pipeline.py:73-85)."""
+    a, b = alpha_t, alpha_tm1
+    sa = a ** 0.5
+    sb = b ** 0.5
+    return sa * ((1 / sb) * x_tm1 + ((1 / a - 1) ** 0.5 - (1 / b - 1) ** 0.5) * eps_xt)
+
+
+def polar_interpolate(x, y, alpha):
+    """Restatement of ``polar_intrtpolate`` (pipeline.py:295-300)."""
+    n0 = x.norm()
+    n1 = y.norm()
+    ll = x * alpha + y * (1 - alpha)
+    n = n0 * alpha + n1 * (1 - alpha)
+    return ll / ll.norm() * n
