@@ -1,0 +1,58 @@
+// C-ABI plumbing: thread-local error string, device gate (sm_100 only; there is no CPU or other-arch fallback).
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace ia2p {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_dev_ok[64];     // 0 unknown, 1 ok, -1 bad
+static int g_sm_count[64];
+
+static int query_device(int dev) {
+  if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return IA2P_E_DEVICE; }
+  if (g_dev_ok[dev] == 0) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return IA2P_E_DEVICE; }
+    g_sm_count[dev] = prop.multiProcessorCount;
+    g_dev_ok[dev] = (prop.major == 10) ? 1 : -1;
+    if (g_dev_ok[dev] < 0) set_error("device %d is sm_%d%d; this library only runs on sm_100 (B200)", dev, prop.major, prop.minor);
+  }
+  if (g_dev_ok[dev] < 0) {
+    set_error("device %d is not sm_100 (B200); no fallback path exists", dev);
+    return IA2P_E_DEVICE;
+  }
+  return 0;
+}
+
+int check_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("cudaGetDevice: %s (no CUDA device: this library has no CPU path)", cudaGetErrorString(e)); return IA2P_E_DEVICE; }
+  return query_device(dev);
+}
+
+int sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || g_sm_count[dev] <= 0) return 148;
+  return g_sm_count[dev];
+}
+
+}  // namespace ia2p
+
+extern "C" int ia2p_version(void) { return 100; }
+extern "C" const char* ia2p_last_error(void) { return ia2p::g_err; }
+extern "C" int ia2p_device_check(int device) {
+  if (device < 0) return ia2p::check_device();
+  return ia2p::query_device(device);
+}

@@ -1,0 +1,320 @@
+// HBM-bound elementwise kernels: fused CFG + DDIM update, inverse-DDIM axpby, prior CFG + DDPM step,
+// sinusoidal embeddings, nearest 2x upsample, conv_in / conv_out (few-channel 3x3 convs at the NCHW boundary).
+#include "common.cuh"
+
+namespace ia2p {
+
+// ---------------------------------------------------------------- CFG + DDIM (one pass over the latents)
+template <typename TE, typename TX, typename TI>
+__global__ void cfg_ddim_kernel(const TE* __restrict__ eps2, const TX* __restrict__ x, TX* __restrict__ x_out,
+                                TI* __restrict__ x_in2, long long total, float g, float cx, float ce) {
+  // total = batch * n; eps_u at [i], eps_c at [total + i]
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float eu = load_as_float(eps2 + i + j), ec = load_as_float(eps2 + total + i + j);
+      const float e = eu + g * (ec - eu);
+      const float v = cx * load_as_float(x + i + j) + ce * e;
+      store_from_float(x_out + i + j, v);
+      if (x_in2 != nullptr) {
+        store_from_float(x_in2 + i + j, v);
+        store_from_float(x_in2 + total + i + j, v);
+      }
+    }
+  }
+}
+
+template <typename TE, typename TX>
+__global__ void axpby_kernel(const TE* __restrict__ eps, const TX* __restrict__ x, TX* __restrict__ out, long long n,
+                             float cx, float ce) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    store_from_float(out + i, cx * load_as_float(x + i) + ce * load_as_float(eps + i));
+}
+
+__global__ void prior_step_kernel(const float* __restrict__ x0_pair, const float* __restrict__ x,
+                                  const float* __restrict__ noise, float* __restrict__ out, long long n, float sqrt_a,
+                                  float sqrt_1ma, float g, float c_x0, float c_x, float sigma) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    const float ec = (xv - sqrt_a * x0_pair[i]) / sqrt_1ma;        // get_eps, cond half first
+    const float eu = (xv - sqrt_a * x0_pair[n + i]) / sqrt_1ma;
+    const float e = eu + g * (ec - eu);
+    const float x0 = (xv - sqrt_1ma * e) / sqrt_a;
+    float v = c_x0 * x0 + c_x * xv;
+    if (noise != nullptr) v += sigma * noise[i];
+    out[i] = v;
+  }
+}
+
+template <typename TO>
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, long long n, int dim, int flip, float shift,
+                                          TO* __restrict__ out) {
+  const int half = dim / 2;
+  const long long total = n * (long long)dim;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / dim;
+    const int c = (int)(idx - r * dim);
+    float v = 0.f;
+    if (c < 2 * half) {
+      const int i = c < half ? c : c - half;
+      const bool is_sin = flip ? (c >= half) : (c < half);
+      const float freq = expf(-9.210340371976184f * (float)i / ((float)half - shift));
+      const float a = t[r] * freq;
+      v = is_sin ? sinf(a) : cosf(a);
+    }
+    store_from_float(out + idx, v);
+  }
+}
+
+__device__ __forceinline__ uint4 load8_as_bf16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ uint4 load8_as_bf16(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  uint4 o;
+  o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+  return o;
+}
+__device__ __forceinline__ uint4 load8_as_bf16(const __half* p) {
+  uint4 o;
+  o.x = pack_bf16x2(__half2float(p[0]), __half2float(p[1])); o.y = pack_bf16x2(__half2float(p[2]), __half2float(p[3]));
+  o.z = pack_bf16x2(__half2float(p[4]), __half2float(p[5])); o.w = pack_bf16x2(__half2float(p[6]), __half2float(p[7]));
+  return o;
+}
+
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, uint4* __restrict__ y, long long batch, int h, int w, int cv) {
+  // cv = C/8 vectors per pixel; output pixel (oy, ox) <- input (oy>>1, ox>>1); output bf16 (conv operand)
+  const long long total = batch * (long long)(2 * h) * (2 * w) * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv);
+    long long pix = idx / cv;
+    const int ox = (int)(pix % (2 * w));
+    pix /= (2 * w);
+    const int oy = (int)(pix % (2 * h));
+    const long long b = pix / (2 * h);
+    y[idx] = load8_as_bf16(x + (((b * h + (oy >> 1)) * w + (ox >> 1)) * cv + c) * 8);
+  }
+}
+
+template <typename T>
+__global__ void cast_bf16_kernel(const T* __restrict__ x, uint4* __restrict__ y, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x)
+    y[i] = load8_as_bf16(x + i * 8);
+}
+
+// ---------------------------------------------------------------- conv_in: NCHW (Cin <= 8) -> NHWC bf16
+// one thread = one output pixel x 8 output channels; weights [Cout,Cin,3,3] fp32 read through L1/constant cache.
+template <typename TX, typename TO>
+__global__ void conv_in_kernel(const TX* __restrict__ x, long long in_batch, long long B, int H, int W, int Cin,
+                               const float* __restrict__ w, const float* __restrict__ bias,
+                               TO* __restrict__ out, int Cout) {
+  const int cgroups = Cout / 8;
+  const long long total = B * (long long)H * W * cgroups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgroups);
+    long long pix = idx / cgroups;
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    const long long bi = b % in_batch;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[cg * 8 + j] : 0.f;
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = yy + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = xx + kx - 1;
+          if (ix < 0 || ix >= W) continue;
+          const float v = load_as_float(x + ((bi * Cin + ci) * H + iy) * (long long)W + ix);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v * __ldg(w + (((cg * 8 + j) * Cin + ci) * 3 + ky) * 3 + kx);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) store_from_float(out + pix * Cout + cg * 8 + j, acc[j]);
+  }
+}
+
+// ---------------------------------------------------------------- conv_out: NHWC bf16 -> NCHW, Cout <= 8
+// one warp = one output pixel; lanes split the (tap, channel) reduction with 16-byte loads; weights [Cout,3,3,Cin] fp32.
+template <typename TO, int COUT>
+__global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, long long B, int H, int W, int Cin,
+                                const float* __restrict__ w, const float* __restrict__ bias, TO* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int cv = Cin / 8;
+  for (long long pix = warp_global; pix < B * (long long)H * W; pix += nwarps) {
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;   // warp-uniform
+      const uint4* xp = reinterpret_cast<const uint4*>(x + ((b * H + iy) * (long long)W + ix) * Cin);
+      for (int v = lane; v < cv; v += 32) {
+        const uint4 xv = __ldg(xp + v);
+        float f[8];
+        float2 t;
+        t = unpack_bf16x2(xv.x); f[0] = t.x; f[1] = t.y;
+        t = unpack_bf16x2(xv.y); f[2] = t.x; f[3] = t.y;
+        t = unpack_bf16x2(xv.z); f[4] = t.x; f[5] = t.y;
+        t = unpack_bf16x2(xv.w); f[6] = t.x; f[7] = t.y;
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+          const float4* wp = reinterpret_cast<const float4*>(w + ((long long)(j * 9 + tap)) * Cin + v * 8);
+          const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+          acc[j] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < COUT; ++j)
+        store_from_float(out + ((b * COUT + j) * H + yy) * (long long)W + xx, acc[j] + (bias ? bias[j] : 0.f));
+    }
+  }
+}
+
+static int grid_for(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace ia2p
+
+using namespace ia2p;
+
+#define DISPATCH_DTYPE(code, T, ...)                                   \
+  switch (code) {                                                      \
+    case IA2P_F32: { using T = float; __VA_ARGS__; break; }            \
+    case IA2P_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }   \
+    case IA2P_F16: { using T = __half; __VA_ARGS__; break; }           \
+    default: set_error("unknown dtype code %d", (int)(code)); return IA2P_E_ARG; \
+  }
+
+extern "C" int ia2p_cfg_ddim_step(const void* eps2, int eps_dtype, const void* x, void* x_out, int x_dtype,
+                                  void* x_in_next2, int xin_dtype, int64_t batch, int64_t n, float g, float c_x,
+                                  float c_e, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(eps2 && x && x_out && batch > 0 && n > 0, IA2P_E_ARG, "cfg_ddim_step: null pointer or empty shape");
+  IA2P_REQUIRE(n % 4 == 0, IA2P_E_SHAPE, "cfg_ddim_step: n=%lld must be a multiple of 4", (long long)n);
+  const long long total = batch * n;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(total / 4, 256);
+  if (x_in_next2 == nullptr) xin_dtype = x_dtype;
+  DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(xin_dtype, TI,
+      (cfg_ddim_kernel<TE, TX, TI><<<grid, 256, 0, st>>>(static_cast<const TE*>(eps2), static_cast<const TX*>(x),
+                                                         static_cast<TX*>(x_out), static_cast<TI*>(x_in_next2), total,
+                                                         g, c_x, c_e)))));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_axpby(const void* eps, int eps_dtype, const void* x, void* x_out, int x_dtype, int64_t n, float c_x,
+                          float c_e, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(eps && x && x_out && n > 0, IA2P_E_ARG, "axpby: null pointer or empty shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n, 256);
+  DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX,
+      (axpby_kernel<TE, TX><<<grid, 256, 0, st>>>(static_cast<const TE*>(eps), static_cast<const TX*>(x),
+                                                  static_cast<TX*>(x_out), n, c_x, c_e))));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_prior_cfg_ddpm_step(const float* x0_pair, const float* x, const float* noise, float* x_out, int64_t n,
+                                        float sqrt_a, float sqrt_1ma, float g, float c_x0, float c_x, float sigma,
+                                        void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x0_pair && x && x_out && n > 0, IA2P_E_ARG, "prior_cfg_ddpm_step: null pointer or empty shape");
+  prior_step_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0_pair, x, noise, x_out, n, sqrt_a,
+                                                                                     sqrt_1ma, g, c_x0, c_x, sigma);
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_timestep_embedding(const float* t, int64_t n, int dim, int flip_sin_to_cos, float shift, void* out,
+                                       int out_dtype, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(t && out && n > 0 && dim > 1, IA2P_E_ARG, "timestep_embedding: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n * dim, 256);
+  DISPATCH_DTYPE(out_dtype, TO,
+      (timestep_embedding_kernel<TO><<<grid, 256, 0, st>>>(t, n, dim, flip_sin_to_cos, shift, static_cast<TO*>(out))));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_upsample2x_nhwc(const void* x, int x_dtype, void* y, int64_t batch, int64_t h, int64_t w, int64_t c, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c > 0, IA2P_E_ARG, "upsample2x: bad arguments");
+  IA2P_REQUIRE(c % 8 == 0, IA2P_E_SHAPE, "upsample2x: C=%lld must be a multiple of 8", (long long)c);
+  const long long total = batch * 4 * h * w * (c / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(total, 256);
+  DISPATCH_DTYPE(x_dtype, TX, (upsample2x_kernel<TX><<<grid, 256, 0, st>>>(static_cast<const TX*>(x), static_cast<uint4*>(y),
+                                                                          batch, (int)h, (int)w, (int)(c / 8))));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_cast_to_bf16(const void* x, int x_dtype, void* y, int64_t n, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && y && n > 0, IA2P_E_ARG, "cast_to_bf16: bad arguments");
+  IA2P_REQUIRE(n % 8 == 0, IA2P_E_SHAPE, "cast_to_bf16: n=%lld must be a multiple of 8", (long long)n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n / 8, 256);
+  DISPATCH_DTYPE(x_dtype, TX, (cast_bf16_kernel<TX><<<grid, 256, 0, st>>>(static_cast<const TX*>(x), static_cast<uint4*>(y), n / 8)));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_conv_in_nchw(const void* x, int x_dtype, int64_t in_batch, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                                 const float* w, const float* bias, void* out, int out_dtype, int64_t Cout, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && w && out && B > 0 && in_batch > 0 && H > 0 && W > 0, IA2P_E_ARG, "conv_in: bad arguments");
+  IA2P_REQUIRE(out_dtype == IA2P_BF16 || out_dtype == IA2P_F32, IA2P_E_ARG, "conv_in: out_dtype must be bf16 or f32");
+  IA2P_REQUIRE(Cin >= 1 && Cin <= 16 && Cout % 8 == 0, IA2P_E_SHAPE, "conv_in: Cin<=16 and Cout%%8==0 required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(B * H * W * (Cout / 8), 256);
+  if (out_dtype == IA2P_BF16) {
+    DISPATCH_DTYPE(x_dtype, TX,
+        (conv_in_kernel<TX, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const TX*>(x), in_batch, B, (int)H, (int)W, (int)Cin,
+                                                                 w, bias, static_cast<__nv_bfloat16*>(out), (int)Cout)));
+  } else {
+    DISPATCH_DTYPE(x_dtype, TX,
+        (conv_in_kernel<TX, float><<<grid, 256, 0, st>>>(static_cast<const TX*>(x), in_batch, B, (int)H, (int)W, (int)Cin, w,
+                                                         bias, static_cast<float*>(out), (int)Cout)));
+  }
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_conv_out_nhwc(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const float* w,
+                                  const float* bias, void* out, int out_dtype, int64_t Cout, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && w && out && B > 0 && H > 0 && W > 0, IA2P_E_ARG, "conv_out: bad arguments");
+  IA2P_REQUIRE(Cin % 8 == 0 && Cout == 4, IA2P_E_SHAPE, "conv_out: Cin%%8==0 and Cout==4 required (got %lld, %lld)", (long long)Cin, (long long)Cout);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(B * H * W * 32, 256);
+  DISPATCH_DTYPE(out_dtype, TO,
+      (conv_out_kernel<TO, 4><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), B, (int)H, (int)W, (int)Cin, w,
+                                                    bias, static_cast<TO*>(out))));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}

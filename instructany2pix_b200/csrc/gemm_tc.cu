@@ -1,0 +1,513 @@
+// tcgen05 / TMEM / TMA "tap-table" implicit GEMM for sm_100a.
+//
+//   out[pixel, n] = epilogue( sum over taps e, channel chunks c of  A_e[pixel shifted by (dx,dy), c*64..] . W[n, wk0_e + c*64..] )
+//
+// One kernel covers: plain Linear (1 tap), K-concat of two sources (2 taps), 3x3 conv pad 1 (9 taps over one 4-D
+// NHWC tensor map; TMA zero-fills the halo), stride-2 conv (9 taps over 4 parity-decimated maps) and a fused 1x1
+// shortcut conv (extra taps over the raw block input).  Reference ops replaced: see include/ia2p.h.
+//
+// CTA = 6 warps: w0 TMA producer, w1 tcgen05.mma issuer (also owns TMEM alloc), w2..w5 epilogue (TMEM -> regs ->
+// bias/rowbias/residual/GEGLU -> bf16 -> global).  Persistent over (m_tile, n_tile); STAGES-deep smem ring
+// (full/empty mbarriers), two TMEM accumulator buffers (tmem_full/tmem_empty) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Tile 128 x BLOCK_N x 64, operands K-major SWIZZLE_128B.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ia2p {
+
+struct TapEntry {
+  int16_t map_id, dx, dy, nchunks;
+  int32_t wk0;
+};
+constexpr int kMaxTaps = 24;
+
+struct alignas(64) TcMaps {
+  CUtensorMap a[4];
+  CUtensorMap w;
+};
+
+struct TcParams {
+  TapEntry taps[kMaxTaps];
+  int ntaps, num_kb;
+  int tw_log2, th_log2;            // M tile = TB x TH x TW output pixels, TB*TH*TW == 128
+  int tiles_x, tiles_y, m_tiles, n_tiles;
+  int Wo, Ho, B;                   // output pixel grid (plain GEMM: Wo = M, Ho = B = 1)
+  int N;                           // GEMM N (pre-GEGLU)
+  int rows_per_batch;              // rowbias row = pixel / rows_per_batch
+  const float* bias;
+  const float* rowbias;
+  const void* residual;            // bf16 or fp32 (res_f32)
+  void* out;                       // bf16 or fp32 (out_f32)
+  long long ldo, ldr;
+  int geglu, out_f32, res_f32;
+};
+
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int A_BYTES = 128 * 128;             // 128 rows x 64 bf16
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.a[0]);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int TB = 128 >> (p.tw_log2 + p.th_log2);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int xt = m_tile % p.tiles_x;
+      const int r = m_tile / p.tiles_x;
+      const int yt = r % p.tiles_y, bt = r / p.tiles_y;
+      const int x0 = xt << p.tw_log2, y0 = yt << p.th_log2, b0 = bt * TB, n0 = n_tile * BLOCK_N;
+      for (int e = 0; e < p.ntaps; ++e) {
+        const TapEntry t = p.taps[e];
+        const CUtensorMap* am = &maps.a[t.map_id];
+        for (int c = 0; c < t.nchunks; ++c) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (lane == 0) {
+            const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            tma_load_4d(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
+            tma_load_2d(a_dst + Cfg::A_BYTES, &maps.w, full_bar(stage), t.wk0 + c * 64, n0);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) per 64-wide K block: +32 B inside the swizzle atom
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(empty_bar(stage));
+          if (kb == p.num_kb - 1) umma_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (4 warps, one output row per thread)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row & ((1 << p.tw_log2) - 1);
+    const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+    const int tb = row >> (p.tw_log2 + p.th_log2);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int xt = m_tile % p.tiles_x;
+      const int r = m_tile / p.tiles_x;
+      const int yt = r % p.tiles_y, bt = r / p.tiles_y;
+      const int x = (xt << p.tw_log2) + tw, y = (yt << p.th_log2) + th, b = bt * TB + tb;
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+      const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+      const int n0 = n_tile * BLOCK_N;
+      const float* rb = (p.rowbias != nullptr && valid) ? p.rowbias + (pix / p.rows_per_batch) * (long long)p.N : nullptr;
+
+      mbar_wait(tfull_bar(buf), use & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N);
+
+      if (!p.geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int n = n0 + c * 32;
+          if (n >= p.N) break;                       // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              }
+            }
+            if (rb != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              }
+            }
+            if (p.residual != nullptr) {
+              if (p.res_f32) {
+                const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + pix * p.ldr + n);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 rv = __ldg(rp + i);
+                  f[4 * i + 0] += rv.x; f[4 * i + 1] += rv.y; f[4 * i + 2] += rv.z; f[4 * i + 3] += rv.w;
+                }
+              } else {
+                const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + n);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 rv = __ldg(rp + i);
+                  float2 t;
+                  t = unpack_bf16x2(rv.x); f[8 * i + 0] += t.x; f[8 * i + 1] += t.y;
+                  t = unpack_bf16x2(rv.y); f[8 * i + 2] += t.x; f[8 * i + 3] += t.y;
+                  t = unpack_bf16x2(rv.z); f[8 * i + 4] += t.x; f[8 * i + 5] += t.y;
+                  t = unpack_bf16x2(rv.w); f[8 * i + 6] += t.x; f[8 * i + 7] += t.y;
+                }
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.ldo + n);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 o;
+                o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+                o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+                o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                op[i] = o;
+              }
+            }
+          }
+        }
+      } else {
+        // GEGLU: W rows interleaved in 32-row groups [value | gate]; out col = n/2 + i:  value * gelu_erf(gate)
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          const int n = n0 + c * 64;
+          if (n >= p.N) break;
+          uint32_t vv[32], vg[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 64), vv);
+          tmem_ld_32x32(t_row + (uint32_t)(c * 64 + 32), vg);
+          tmem_ld_wait();
+          if (valid) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float a = __uint_as_float(vv[i]), g = __uint_as_float(vg[i]);
+              if (p.bias != nullptr) { a += __ldg(p.bias + n + i); g += __ldg(p.bias + n + 32 + i); }
+              f[i] = a * gelu_erf_f(g);
+            }
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + (n >> 1));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+              o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+              o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+              o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+              op[i] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  // ------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ================================================================ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// bf16 tensor map, rank <= 4, dims/strides innermost-first; strides in ELEMENTS (stride of dim 0 is 1).
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                    const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  IA2P_REQUIRE(enc != nullptr, IA2P_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_el[i] * 2;
+      IA2P_REQUIRE(gstr[i - 1] % 16 == 0, IA2P_E_ALIGN, "tensor-map stride %llu B not a multiple of 16", (unsigned long long)gstr[i - 1]);
+    }
+  }
+  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IA2P_E_ALIGN, "tensor-map base not 16-byte aligned");
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IA2P_REQUIRE(r == CUDA_SUCCESS, IA2P_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+static int pick_block_n(int64_t N, bool geglu) {
+  if (geglu) return (N % 256 == 0) ? 256 : 128;
+  if (N % 256 == 0) return 256;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0 || N > 128) return 128;
+  return 128;
+}
+
+template <int BN>
+static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_done = false;   // benign race: idempotent
+  if (!attr_done) {
+    IA2P_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  p.n_tiles = (p.N + BN - 1) / BN;
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  tc_gemm_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, p);
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+static int dispatch_tc(const TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_tc<256>(maps, p, st);
+    case 160: return launch_tc<160>(maps, p, st);
+    default: return launch_tc<128>(maps, p, st);
+  }
+}
+
+static int make_w_map(TcMaps& maps, const void* W, int64_t N, int64_t Ktot, int bn) {
+  const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
+  const uint64_t str[2] = {1, (uint64_t)Ktot};
+  const uint32_t box[2] = {64, (uint32_t)bn};
+  return make_map(&maps.w, W, 2, dims, str, box);
+}
+
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+}  // namespace ia2p
+
+using namespace ia2p;
+
+extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
+                              const void* W, void* out, int64_t ldo, int64_t M, int64_t N,
+                              const float* bias, const float* rowbias, int64_t rows_per_batch,
+                              const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(A && W && out && M > 0 && N > 0 && K1 > 0, IA2P_E_ARG, "gemm: null pointer or empty shape");
+  IA2P_REQUIRE((out_dtype == IA2P_BF16 || out_dtype == IA2P_F32) && (residual == nullptr || res_dtype == IA2P_BF16 || res_dtype == IA2P_F32),
+               IA2P_E_ARG, "gemm: out/residual dtype must be bf16 or f32");
+  IA2P_REQUIRE(K1 % 64 == 0 && K2 % 64 == 0 && K2 >= 0, IA2P_E_SHAPE, "gemm: K1=%lld K2=%lld must be multiples of 64", (long long)K1, (long long)K2);
+  IA2P_REQUIRE(N % 32 == 0, IA2P_E_SHAPE, "gemm: N=%lld must be a multiple of 32", (long long)N);
+  IA2P_REQUIRE(lda % 8 == 0 && ldo % 8 == 0 && (A2 == nullptr || lda2 % 8 == 0) && (residual == nullptr || ldr % 8 == 0),
+               IA2P_E_ALIGN, "gemm: leading dimensions must be multiples of 8 elements");
+  IA2P_REQUIRE((A2 == nullptr) == (K2 == 0), IA2P_E_ARG, "gemm: A2 and K2 must be given together");
+  const bool geglu = epilogue == IA2P_EPI_GEGLU;
+  IA2P_REQUIRE(!geglu || (N % 64 == 0 && residual == nullptr && rowbias == nullptr && out_dtype == IA2P_BF16), IA2P_E_ARG, "gemm: GEGLU needs N%%64==0, bf16 output and no residual/rowbias");
+  IA2P_REQUIRE(rowbias == nullptr || rows_per_batch > 0, IA2P_E_ARG, "gemm: rowbias needs rows_per_batch");
+  IA2P_REQUIRE(M < (1ll << 31) && N < (1ll << 31), IA2P_E_SHAPE, "gemm: M/N too large");
+
+  const int bn = pick_block_n(N, geglu);
+  TcMaps maps;
+  TcParams p{};
+  {
+    const uint64_t dims[4] = {(uint64_t)K1, (uint64_t)M, 1, 1};
+    const uint64_t str[4] = {1, (uint64_t)lda, (uint64_t)lda * (uint64_t)M, (uint64_t)lda * (uint64_t)M};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int e = make_map(&maps.a[0], A, 4, dims, str, box)) return e;
+    maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+  }
+  p.taps[0] = TapEntry{0, 0, 0, (int16_t)(K1 / 64), 0};
+  p.ntaps = 1;
+  if (A2 != nullptr) {
+    const uint64_t dims[4] = {(uint64_t)K2, (uint64_t)M, 1, 1};
+    const uint64_t str[4] = {1, (uint64_t)lda2, (uint64_t)lda2 * (uint64_t)M, (uint64_t)lda2 * (uint64_t)M};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int e = make_map(&maps.a[1], A2, 4, dims, str, box)) return e;
+    p.taps[1] = TapEntry{1, 0, 0, (int16_t)(K2 / 64), (int32_t)K1};
+    p.ntaps = 2;
+  }
+  if (int e = make_w_map(maps, W, N, K1 + K2, bn)) return e;
+  p.num_kb = (int)((K1 + K2) / 64);
+  p.tw_log2 = 7; p.th_log2 = 0;
+  p.tiles_x = (int)((M + 127) / 128); p.tiles_y = 1;
+  p.m_tiles = p.tiles_x;
+  p.Wo = (int)M; p.Ho = 1; p.B = 1;
+  p.N = (int)N;
+  p.rows_per_batch = rowbias ? (int)rows_per_batch : 1;
+  p.bias = bias; p.rowbias = rowbias;
+  p.residual = residual;
+  p.out = out;
+  p.ldo = ldo; p.ldr = ldr; p.geglu = geglu ? 1 : 0;
+  p.out_f32 = out_dtype == IA2P_F32; p.res_f32 = res_dtype == IA2P_F32;
+  return dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int stride,
+                                      const void* w, const void* sc_a, int64_t sc_ca, const void* sc_b, int64_t sc_cb,
+                                      void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
+                                      const void* residual, int res_dtype, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE((out_dtype == IA2P_BF16 || out_dtype == IA2P_F32) && (residual == nullptr || res_dtype == IA2P_BF16 || res_dtype == IA2P_F32),
+               IA2P_E_ARG, "conv3x3: out/residual dtype must be bf16 or f32");
+  IA2P_REQUIRE(x && w && out && B > 0 && H > 0 && W > 0, IA2P_E_ARG, "conv3x3: null pointer or empty shape");
+  IA2P_REQUIRE(stride == 1 || stride == 2, IA2P_E_ARG, "conv3x3: stride must be 1 or 2");
+  IA2P_REQUIRE(Cin % 64 == 0 && sc_ca % 64 == 0 && sc_cb % 64 == 0, IA2P_E_SHAPE, "conv3x3: channel counts must be multiples of 64 (Cin=%lld)", (long long)Cin);
+  IA2P_REQUIRE(Cout % 32 == 0, IA2P_E_SHAPE, "conv3x3: Cout=%lld must be a multiple of 32", (long long)Cout);
+  IA2P_REQUIRE((sc_a == nullptr) == (sc_ca == 0) && (sc_b == nullptr) == (sc_cb == 0) && (sc_b == nullptr || sc_a != nullptr),
+               IA2P_E_ARG, "conv3x3: inconsistent shortcut sources");
+  IA2P_REQUIRE(stride == 1 || (sc_a == nullptr && H % 2 == 0 && W % 2 == 0), IA2P_E_ARG, "conv3x3: stride 2 needs even H,W and no shortcut");
+  const int64_t Ho = H / stride, Wo = W / stride;
+  // tile: largest power-of-two divisors
+  int TW = 1; while (TW < 128 && Wo % (TW * 2) == 0) TW *= 2;
+  int TH = 1; while (TW * TH < 128 && Ho % (TH * 2) == 0) TH *= 2;
+  const int TB = 128 / (TW * TH);
+  const int64_t Ktot = 9 * Cin + sc_ca + sc_cb;
+  const int bn = pick_block_n(Cout, false);
+
+  TcMaps maps;
+  TcParams p{};
+  const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  int nt = 0;
+  if (stride == 1) {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)(W * Cin), (uint64_t)(H * W * Cin)};
+    if (int e = make_map(&maps.a[0], xb, 4, dims, str, box)) return e;
+    maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx)
+        p.taps[nt++] = TapEntry{0, (int16_t)(kx - 1), (int16_t)(ky - 1), (int16_t)(Cin / 64), (int32_t)((ky * 3 + kx) * Cin)};
+    const void* srcs[2] = {sc_a, sc_b};
+    const int64_t cs[2] = {sc_ca, sc_cb};
+    int64_t koff = 9 * Cin;
+    for (int s = 0; s < 2; ++s) {
+      if (srcs[s] == nullptr) continue;
+      const uint64_t d2[4] = {(uint64_t)cs[s], (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      const uint64_t s2[4] = {1, (uint64_t)cs[s], (uint64_t)(W * cs[s]), (uint64_t)(H * W * cs[s])};
+      if (int e = make_map(&maps.a[1 + s], srcs[s], 4, d2, s2, box)) return e;
+      p.taps[nt++] = TapEntry{(int16_t)(1 + s), 0, 0, (int16_t)(cs[s] / 64), (int32_t)koff};
+      koff += cs[s];
+    }
+  } else {
+    // x = 2*xo + px: one decimated view per parity (py, px); tap k in {0,1,2} reads parity (k==1 ? 0 : 1) at offset (k==0 ? -1 : 0)
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+        const uint64_t str[4] = {1, (uint64_t)(2 * Cin), (uint64_t)(2 * W * Cin), (uint64_t)(H * W * Cin)};
+        if (int e = make_map(&maps.a[py * 2 + px], xb + (py * W + px) * Cin, 4, dims, str, box)) return e;
+      }
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int py = ky == 1 ? 0 : 1, px = kx == 1 ? 0 : 1;
+        p.taps[nt++] = TapEntry{(int16_t)(py * 2 + px), (int16_t)(kx == 0 ? -1 : 0), (int16_t)(ky == 0 ? -1 : 0),
+                                (int16_t)(Cin / 64), (int32_t)((ky * 3 + kx) * Cin)};
+      }
+  }
+  p.ntaps = nt;
+  if (int e = make_w_map(maps, w, Cout, Ktot, bn)) return e;
+  p.num_kb = (int)(Ktot / 64);
+  p.tw_log2 = ilog2_exact(TW); p.th_log2 = ilog2_exact(TH);
+  p.tiles_x = (int)(Wo / TW); p.tiles_y = (int)(Ho / TH);
+  p.m_tiles = p.tiles_x * p.tiles_y * (int)((B + TB - 1) / TB);
+  p.Wo = (int)Wo; p.Ho = (int)Ho; p.B = (int)B;
+  p.N = (int)Cout;
+  p.rows_per_batch = (int)(Ho * Wo);
+  p.bias = bias; p.rowbias = rowbias;
+  p.residual = residual;
+  p.out = out;
+  p.ldo = Cout; p.ldr = Cout; p.geglu = 0;
+  p.out_f32 = out_dtype == IA2P_F32; p.res_f32 = res_dtype == IA2P_F32;
+  return dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,248 @@
+// HBM-bound normalisation kernels: GroupNorm (NHWC, optional two-source channel concat, optional fused SiLU) and
+// LayerNorm (warp per row, two-pass statistics in registers).  bf16 I/O, fp32 math, fp64 cross-CTA accumulation.
+#include "common.cuh"
+
+namespace ia2p {
+
+// ---------------------------------------------------------------- 8-element vector load/store helpers
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    float2 t;
+    t = unpack_bf16x2(v.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(v.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(v.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(v.w); f[6] = t.x; f[7] = t.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+// ---------------------------------------------------------------- GroupNorm statistics
+// grid (slabs, batch); block (CV = C/8 vector lanes, ROWS pixel lanes).  Every thread owns one 8-channel vector
+// column and strides over the slab's pixels; per-channel partials are folded across ROWS in shared memory, then
+// per-group sums go to global fp64 atomics.
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
+                                long long hw, int groups, int pix_per_slab, double* __restrict__ stats) {
+  extern __shared__ float sm[];   // [2][C]
+  const int C = ca + cb;
+  const int cv = threadIdx.x;     // vector index within the pixel
+  const int c0 = cv * 8;
+  const long long b = blockIdx.y;
+  const long long p_begin = (long long)blockIdx.x * pix_per_slab;
+  long long p_end = p_begin + pix_per_slab;
+  if (p_end > hw) p_end = hw;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) sm[i] = 0.f;
+  __syncthreads();
+
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  const bool from_a = c0 < ca;
+  const T* src = from_a ? xa + b * hw * ca + c0 : xb + b * hw * cb + (c0 - ca);
+  const int ld = from_a ? ca : cb;
+  for (long long p = p_begin + threadIdx.y; p < p_end; p += blockDim.y) {
+    float f[8];
+    Vec8<T>::load(src + p * ld, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm[c0 + j], s[j]);
+    atomicAdd(&sm[C + c0 + j], ss[j]);
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.y * blockDim.x + threadIdx.x; g < groups; g += blockDim.x * blockDim.y) {
+    double a = 0.0, q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += (double)sm[c]; q += (double)sm[C + c]; }
+    atomicAdd(&stats[(b * groups + g) * 2 + 0], a);
+    atomicAdd(&stats[(b * groups + g) * 2 + 1], q);
+  }
+}
+
+// ---------------------------------------------------------------- GroupNorm apply (+SiLU)
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw, long long hw, int groups,
+                                float eps, int silu, int pix_per_slab, const double* __restrict__ stats) {
+  extern __shared__ float sm[];   // scale[C], shift[C]
+  const int C = ca + cb;
+  const int cpg = C / groups;
+  const long long b = blockIdx.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const double cnt = (double)hw * cpg;
+  for (int c = tid; c < C; c += nthr) {
+    const int g = c / cpg;
+    const double mean = stats[(b * groups + g) * 2] / cnt;
+    double var = stats[(b * groups + g) * 2 + 1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = rstd * gamma[c];
+    sm[c] = sc;
+    sm[C + c] = beta[c] - (float)mean * sc;
+  }
+  __syncthreads();
+  const int c0 = threadIdx.x * 8;
+  const bool from_a = c0 < ca;
+  const T* src = from_a ? xa + b * hw * ca + c0 : xb + b * hw * cb + (c0 - ca);
+  const int ld = from_a ? ca : cb;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = sm[c0 + j]; sh[j] = sm[C + c0 + j]; }
+  const long long p_begin = (long long)blockIdx.x * pix_per_slab;
+  long long p_end = p_begin + pix_per_slab;
+  if (p_end > hw) p_end = hw;
+  for (long long p = p_begin + threadIdx.y; p < p_end; p += blockDim.y) {
+    float f[8];
+    Vec8<T>::load(src + p * ld, f);
+    if (raw != nullptr) Vec8<__nv_bfloat16>::store(raw + (b * hw + p) * C + c0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = f[j] * sc[j] + sh[j];
+      if (silu) f[j] = silu_f(f[j]);
+    }
+    Vec8<__nv_bfloat16>::store(y + (b * hw + p) * C + c0, f);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm (warp per row)
+template <typename T, typename TO, int MAXV>
+__global__ void layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 TO* __restrict__ y, long long rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const int nv = cols / 8;
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+      Vec8<T>::load(x + row * cols + v * 8, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+      float o[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * g[j] + bb[j];
+      Vec8<TO>::store(y + row * cols + v * 8, o);
+    }
+  }
+}
+
+template <typename T, typename TO>
+static int launch_ln(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t cols, float eps,
+                     cudaStream_t st) {
+  const int block = 256;
+  const long long grid = (rows * 32 + block - 1) / block;
+  const T* xp = static_cast<const T*>(x);
+  TO* yp = static_cast<TO*>(y);
+  if (cols <= 8 * 32 * 2) layernorm_kernel<T, TO, 2><<<(unsigned)grid, block, 0, st>>>(xp, gamma, beta, yp, rows, (int)cols, eps);
+  else if (cols <= 8 * 32 * 5) layernorm_kernel<T, TO, 5><<<(unsigned)grid, block, 0, st>>>(xp, gamma, beta, yp, rows, (int)cols, eps);
+  else layernorm_kernel<T, TO, 8><<<(unsigned)grid, block, 0, st>>>(xp, gamma, beta, yp, rows, (int)cols, eps);
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ia2p
+
+using namespace ia2p;
+
+extern "C" int64_t ia2p_groupnorm_workspace_bytes(int64_t batch, int groups) { return batch * groups * 2 * (int64_t)sizeof(double); }
+
+extern "C" int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, int64_t cb, int x_dtype, const float* gamma,
+                                   const float* beta, void* y, void* raw, int64_t batch, int64_t hw, int groups, float eps,
+                                   int silu, void* workspace, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x_dtype == IA2P_BF16 || x_dtype == IA2P_F32, IA2P_E_ARG, "groupnorm: x_dtype must be bf16 or f32");
+  IA2P_REQUIRE(xa && gamma && beta && y && workspace && batch > 0 && hw > 0 && groups > 0, IA2P_E_ARG, "groupnorm: bad arguments");
+  IA2P_REQUIRE((xb == nullptr) == (cb == 0), IA2P_E_ARG, "groupnorm: xb and cb must be given together");
+  const int64_t C = ca + cb;
+  IA2P_REQUIRE(ca % 8 == 0 && cb % 8 == 0 && C % groups == 0, IA2P_E_SHAPE, "groupnorm: ca=%lld cb=%lld groups=%d unsupported", (long long)ca, (long long)cb, groups);
+  IA2P_REQUIRE(C / 8 <= 1024 && C * 8 <= 48 * 1024, IA2P_E_SHAPE, "groupnorm: C=%lld too large", (long long)C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cv = (int)(C / 8);
+  int rows = 512 / cv;
+  if (rows < 1) rows = 1;
+  if (rows > 32) rows = 32;
+  // enough slabs for ~4 CTAs per SM, at least `rows*4` pixels each
+  long long slabs = ((long long)sm_count() * 4 + batch - 1) / batch;
+  long long max_slabs = (hw + rows * 4 - 1) / (rows * 4);
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  const int pps = (int)((hw + slabs - 1) / slabs);
+  slabs = (hw + pps - 1) / pps;
+  const dim3 block(cv, rows), grid((unsigned)slabs, (unsigned)batch);
+  const size_t smem = 2 * C * sizeof(float);
+  double* stats = static_cast<double*>(workspace);
+  IA2P_CUDA(cudaMemsetAsync(stats, 0, (size_t)ia2p_groupnorm_workspace_bytes(batch, groups), st));
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  __nv_bfloat16* rp = static_cast<__nv_bfloat16*>(raw);
+  if (x_dtype == IA2P_BF16) {
+    const __nv_bfloat16 *a = static_cast<const __nv_bfloat16*>(xa), *b = static_cast<const __nv_bfloat16*>(xb);
+    gn_stats_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, hw, groups, pps, stats);
+    IA2P_LAUNCH_CHECK();
+    gn_apply_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
+  } else {
+    const float *a = static_cast<const float*>(xa), *b = static_cast<const float*>(xb);
+    gn_stats_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, hw, groups, pps, stats);
+    IA2P_LAUNCH_CHECK();
+    gn_apply_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
+  }
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+                              int64_t rows, int64_t cols, float eps, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && gamma && beta && y && rows > 0 && cols > 0, IA2P_E_ARG, "layernorm: bad arguments");
+  IA2P_REQUIRE(cols % 8 == 0 && cols <= 2048, IA2P_E_SHAPE, "layernorm: cols=%lld must be a multiple of 8 and <= 2048", (long long)cols);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == IA2P_BF16 && y_dtype == IA2P_BF16) return launch_ln<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, y, rows, cols, eps, st);
+  if (x_dtype == IA2P_F32 && y_dtype == IA2P_BF16) return launch_ln<float, __nv_bfloat16>(x, gamma, beta, y, rows, cols, eps, st);
+  if (x_dtype == IA2P_F32 && y_dtype == IA2P_F32) return launch_ln<float, float>(x, gamma, beta, y, rows, cols, eps, st);
+  set_error("layernorm: unsupported dtype pair (%d -> %d)", x_dtype, y_dtype);
+  return IA2P_E_ARG;
+}

@@ -1,0 +1,344 @@
+"""Torch-tensor front end of the C ABI (``include/ia2p.h``).
+
+Each function validates device/dtype/layout, allocates the output with torch (the library never allocates), passes raw
+device pointers + the CURRENT torch stream to ``libia2p_sm100a.so`` and returns the output tensor.  No op here has a
+PyTorch/CPU implementation: a missing library or a non-sm_100 device raises ``IA2PError``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_NEW, ACT_NONE, ACT_SILU, BF16, F16, F32, IA2PError  # noqa: F401
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need(t, dtype, name, ndim=None):
+    if not t.is_cuda:
+        raise IA2PError(f"{name}: expected a CUDA tensor (instructany2pix_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise IA2PError(f"{name}: expected {dtype}, got {t.dtype}")
+    if ndim is not None and t.ndim != ndim:
+        raise IA2PError(f"{name}: expected {ndim} dims, got {tuple(t.shape)}")
+    return t
+
+
+def _rows(t, name):
+    """2-D view with unit inner stride -> (tensor, leading dimension)."""
+    if t.ndim != 2 or t.stride(1) != 1:
+        raise IA2PError(f"{name}: expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} stride {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise IA2PError(f"{what}: expected a CUDA tensor; instructany2pix_b200 has no CPU path")
+
+
+def _f32(t, name):
+    return None if t is None else _need(t, torch.float32, name).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ sampler epilogues
+def cfg_ddim_step(eps2, x, g, c_x, c_e, x_out=None, x_in_next2=None):
+    """x_out = c_x*x + c_e*(eps_u + g*(eps_c - eps_u)); eps2 = [uncond; cond] (custom_pipelines.py:348-357)."""
+    lib = _lib.load()
+    eps2, x = eps2.contiguous(), x.contiguous()
+    batch = x.shape[0]
+    n = x.numel() // batch
+    assert eps2.numel() == 2 * x.numel()
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    _lib.check(lib.ia2p_cfg_ddim_step(eps2.data_ptr(), _DT[eps2.dtype], x.data_ptr(), x_out.data_ptr(), _DT[x.dtype],
+                                      _ptr(x_in_next2), _DT[x_in_next2.dtype] if x_in_next2 is not None else F32,
+                                      batch, n, float(g), float(c_x), float(c_e), _stream()), "cfg_ddim_step")
+    return x_out
+
+
+def axpby(eps, x, c_x, c_e, out=None):
+    """out = c_x*x + c_e*eps (inverse DDIM step, pnp_pipeline.py:73-85)."""
+    lib = _lib.load()
+    eps, x = eps.contiguous(), x.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.ia2p_axpby(eps.data_ptr(), _DT[eps.dtype], x.data_ptr(), out.data_ptr(), _DT[x.dtype], x.numel(),
+                              float(c_x), float(c_e), _stream()), "axpby")
+    return out
+
+
+def prior_cfg_ddpm_step(x0_pair, x, noise, sqrt_a, sqrt_1ma, g, c_x0, c_x, sigma, out=None):
+    lib = _lib.load()
+    x0_pair, x = _f32(x0_pair, "x0_pair"), _f32(x, "x")
+    noise = _f32(noise, "noise")
+    n = x.numel()
+    assert x0_pair.numel() == 2 * n
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.ia2p_prior_cfg_ddpm_step(x0_pair.data_ptr(), x.data_ptr(), _ptr(noise), out.data_ptr(), n, float(sqrt_a),
+                                            float(sqrt_1ma), float(g), float(c_x0), float(c_x), float(sigma), _stream()),
+               "prior_cfg_ddpm_step")
+    return out
+
+
+def timestep_embedding(t, dim, flip_sin_to_cos=True, shift=0.0, dtype=torch.float32):
+    lib = _lib.load()
+    t = _f32(t.reshape(-1), "t")
+    out = torch.empty(t.numel(), dim, device=t.device, dtype=dtype)
+    _lib.check(lib.ia2p_timestep_embedding(t.data_ptr(), t.numel(), dim, int(flip_sin_to_cos), float(shift), out.data_ptr(),
+                                           _DT[dtype], _stream()), "timestep_embedding")
+    return out
+
+
+def to_bf16(x):
+    """bf16 copy of a stream tensor (tensor-core operand); identity for bf16 input."""
+    if x.dtype == torch.bfloat16:
+        return x
+    lib = _lib.load()
+    require_cuda(x, "to_bf16")
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.ia2p_cast_to_bf16(x.data_ptr(), _DT[x.dtype], y.data_ptr(), x.numel(), _stream()), "cast_to_bf16")
+    return y
+
+
+def upsample2x(x):
+    """nearest 2x upsample of an NHWC tensor (fp32|bf16) -> bf16."""
+    lib = _lib.load()
+    require_cuda(x, "upsample2x")
+    assert x.ndim == 4
+    x = x.contiguous()
+    b, h, w, c = x.shape
+    y = torch.empty(b, 2 * h, 2 * w, c, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.ia2p_upsample2x_nhwc(x.data_ptr(), _DT[x.dtype], y.data_ptr(), b, h, w, c, _stream()), "upsample2x")
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ norms
+_GN_WS = {}
+
+
+def groupnorm(xa, xb, gamma, beta, groups, eps, silu, want_raw=False):
+    """GroupNorm(+SiLU) over the channel concat [xa | xb] of NHWC tensors [B, ..., C] (fp32 or bf16) -> bf16.
+    ``want_raw``: also return the un-normalised concat as bf16 (operand of the fused 1x1 shortcut conv)."""
+    lib = _lib.load()
+    require_cuda(xa, "groupnorm")
+    if xa.dtype not in (torch.bfloat16, torch.float32):
+        raise IA2PError(f"groupnorm: unsupported dtype {xa.dtype}")
+    xa = xa.contiguous()
+    b, ca = xa.shape[0], xa.shape[-1]
+    hw = xa.numel() // (b * ca)
+    cb = 0
+    if xb is not None:
+        xb = _need(xb, xa.dtype, "xb").contiguous()
+        cb = xb.shape[-1]
+        assert xb.numel() // (b * cb) == hw
+    gamma, beta = _f32(gamma, "gamma"), _f32(beta, "beta")
+    out = torch.empty(*xa.shape[:-1], ca + cb, device=xa.device, dtype=torch.bfloat16)
+    raw = torch.empty_like(out) if want_raw else None
+    key = (xa.device, torch.cuda.current_stream().cuda_stream)
+    need = lib.ia2p_groupnorm_workspace_bytes(b, groups)
+    ws = _GN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 4096), device=xa.device, dtype=torch.uint8)
+        _GN_WS[key] = ws
+    _lib.check(lib.ia2p_groupnorm_nhwc(xa.data_ptr(), ca, _ptr(xb), cb, _DT[xa.dtype], gamma.data_ptr(), beta.data_ptr(),
+                                       out.data_ptr(), _ptr(raw), b, hw, groups, float(eps), int(silu), ws.data_ptr(),
+                                       _stream()), "groupnorm")
+    return (out, raw) if want_raw else out
+
+
+def layernorm(x, gamma, beta, eps, out_dtype=None):
+    """LayerNorm over the last dim; (in,out) in {(bf16,bf16), (fp32,bf16), (fp32,fp32)}."""
+    lib = _lib.load()
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise IA2PError(f"layernorm: unsupported dtype {x.dtype}")
+    require_cuda(x, "layernorm")
+    out_dtype = out_dtype or x.dtype
+    x = x.contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    gamma, beta = _f32(gamma, "gamma"), _f32(beta, "beta")
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    _lib.check(lib.ia2p_layernorm(x.data_ptr(), _DT[x.dtype], gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                  _DT[out_dtype], rows, cols, float(eps), _stream()), "layernorm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core GEMM / conv
+def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None, geglu=False, out=None,
+         out_dtype=torch.bfloat16):
+    """out = epilogue([a | a2] @ w^T).  a: [M,K1] bf16 (row-strided view allowed), w: [N,K1+K2] bf16 contiguous;
+    residual bf16|fp32, out bf16|fp32 (fp32 = residual-stream tensors)."""
+    lib = _lib.load()
+    _need(a, torch.bfloat16, "a", 2)
+    _need(w, torch.bfloat16, "w", 2)
+    assert w.is_contiguous()
+    M, K1 = a.shape
+    N = w.shape[0]
+    lda = _rows(a, "a")
+    K2, lda2 = 0, 0
+    if a2 is not None:
+        _need(a2, torch.bfloat16, "a2", 2)
+        assert a2.shape[0] == M
+        K2, lda2 = a2.shape[1], _rows(a2, "a2")
+    assert w.shape[1] == K1 + K2, (w.shape, K1, K2)
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty(M, n_out, device=a.device, dtype=out_dtype)
+    else:
+        require_cuda(out, "gemm(out)")
+        assert out.shape == (M, n_out) and out.dtype in (torch.bfloat16, torch.float32)
+    ldo = _rows(out, "out")
+    ldr, res_dt = 0, BF16
+    if residual is not None:
+        require_cuda(residual, "gemm(residual)")
+        assert residual.shape == (M, n_out) and residual.dtype in (torch.bfloat16, torch.float32)
+        ldr, res_dt = _rows(residual, "residual"), _DT[residual.dtype]
+    bias, rowbias = _f32(bias, "bias"), _f32(rowbias, "rowbias")
+    _lib.check(lib.ia2p_gemm_bf16(a.data_ptr(), lda, K1, _ptr(a2), lda2, K2, w.data_ptr(), out.data_ptr(), ldo, M, N,
+                                  _ptr(bias), _ptr(rowbias), int(rows_per_batch), _ptr(residual), ldr, res_dt,
+                                  _DT[out.dtype], _lib.EPI_GEGLU if geglu else _lib.EPI_NONE, _stream()), "gemm_bf16")
+    return out
+
+
+def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None, residual=None, out_dtype=torch.bfloat16):
+    """3x3 pad-1 conv on NHWC bf16; w: [cout, 9*Cin + Csc] bf16, K order (ky,kx,cin) then shortcut channels;
+    residual bf16|fp32, out bf16|fp32."""
+    lib = _lib.load()
+    _need(x, torch.bfloat16, "x", 4)
+    _need(w, torch.bfloat16, "w", 2)
+    x = x.contiguous()
+    assert w.is_contiguous()
+    B, H, W, Cin = x.shape
+    ca = cb = 0
+    if sc_a is not None:
+        sc_a = _need(sc_a, torch.bfloat16, "sc_a", 4).contiguous()
+        ca = sc_a.shape[-1]
+    if sc_b is not None:
+        sc_b = _need(sc_b, torch.bfloat16, "sc_b", 4).contiguous()
+        cb = sc_b.shape[-1]
+    assert w.shape == (cout, 9 * Cin + ca + cb), (tuple(w.shape), cout, Cin, ca, cb)
+    Ho, Wo = H // stride, W // stride
+    out = torch.empty(B, Ho, Wo, cout, device=x.device, dtype=out_dtype)
+    res_dt = BF16
+    if residual is not None:
+        require_cuda(residual, "conv3x3(residual)")
+        residual = residual.contiguous()
+        assert residual.shape == out.shape and residual.dtype in (torch.bfloat16, torch.float32)
+        res_dt = _DT[residual.dtype]
+    bias, rowbias = _f32(bias, "bias"), _f32(rowbias, "rowbias")
+    _lib.check(lib.ia2p_conv3x3_nhwc_bf16(x.data_ptr(), B, H, W, Cin, stride, w.data_ptr(), _ptr(sc_a), ca, _ptr(sc_b), cb,
+                                          out.data_ptr(), _DT[out_dtype], cout, _ptr(bias), _ptr(rowbias), _ptr(residual),
+                                          res_dt, _stream()), "conv3x3")
+    return out
+
+
+def conv_in(x_nchw, w, bias, out_batch=None, out_dtype=torch.bfloat16):
+    """conv_in from NCHW latents to NHWC (bf16|fp32); batch read modulo x.shape[0] (CFG duplication)."""
+    lib = _lib.load()
+    if not x_nchw.is_cuda:
+        raise IA2PError("conv_in: expected a CUDA tensor")
+    x_nchw = x_nchw.contiguous()
+    in_b, cin, H, W = x_nchw.shape
+    B = out_batch or in_b
+    w, bias = _f32(w, "w"), _f32(bias, "bias")
+    cout = w.shape[0]
+    out = torch.empty(B, H, W, cout, device=x_nchw.device, dtype=out_dtype)
+    _lib.check(lib.ia2p_conv_in_nchw(x_nchw.data_ptr(), _DT[x_nchw.dtype], in_b, B, H, W, cin, w.data_ptr(), _ptr(bias),
+                                     out.data_ptr(), _DT[out_dtype], cout, _stream()), "conv_in")
+    return out
+
+
+def conv_out(x, w, bias, out_dtype=torch.float32):
+    """conv_out from NHWC bf16 to NCHW; w: fp32 [cout, 3, 3, Cin]."""
+    lib = _lib.load()
+    _need(x, torch.bfloat16, "x", 4)
+    x = x.contiguous()
+    B, H, W, Cin = x.shape
+    w, bias = _f32(w, "w"), _f32(bias, "bias")
+    cout = w.shape[0]
+    out = torch.empty(B, cout, H, W, device=x.device, dtype=out_dtype)
+    _lib.check(lib.ia2p_conv_out_nhwc(x.data_ptr(), B, H, W, Cin, w.data_ptr(), _ptr(bias), out.data_ptr(), _DT[out_dtype],
+                                      cout, _stream()), "conv_out")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def flash_self_attn(qkv, batch, n_tokens, heads, out=None):
+    """qkv: [batch*n_tokens, 3*C] bf16 (q | k | v); returns [batch*n_tokens, C]."""
+    lib = _lib.load()
+    _need(qkv, torch.bfloat16, "qkv", 2)
+    C = heads * 64
+    assert qkv.shape == (batch * n_tokens, 3 * C) and qkv.stride(1) == 1
+    ld = qkv.stride(0)
+    if out is None:
+        out = torch.empty(batch * n_tokens, C, device=qkv.device, dtype=torch.bfloat16)
+    es = qkv.element_size()
+    _lib.check(lib.ia2p_flash_self_attn_bf16(qkv.data_ptr(), qkv.data_ptr() + C * es, qkv.data_ptr() + 2 * C * es, ld,
+                                             out.data_ptr(), out.stride(0), batch, n_tokens, heads, 0.125, _stream()),
+               "flash_self_attn")
+    return out
+
+
+def cross_attn(q, kv_text, n_text, kv_ip, n_ip, ip_scale, batch, n_q, heads, out=None):
+    """Decoupled cross-attention.  q: [batch*n_q, C]; kv_text: [batch*n_text, 2C] (k | v); kv_ip: [batch*n_ip, 2C] | None."""
+    lib = _lib.load()
+    _need(q, torch.bfloat16, "q", 2)
+    _need(kv_text, torch.bfloat16, "kv_text", 2)
+    C = heads * 64
+    assert q.shape == (batch * n_q, C) and kv_text.shape == (batch * n_text, 2 * C)
+    es = 2
+    if n_ip > 0:
+        _need(kv_ip, torch.bfloat16, "kv_ip", 2)
+        assert kv_ip.shape == (batch * n_ip, 2 * C)
+        kip, vip, ldip = kv_ip.data_ptr(), kv_ip.data_ptr() + C * es, kv_ip.stride(0)
+    else:
+        kip, vip, ldip = 0, 0, 0
+    if out is None:
+        out = torch.empty(batch * n_q, C, device=q.device, dtype=torch.bfloat16)
+    _lib.check(lib.ia2p_decoupled_cross_attn_bf16(q.data_ptr(), q.stride(0), kv_text.data_ptr(), kv_text.data_ptr() + C * es,
+                                                  kv_text.stride(0), n_text, kip, vip, ldip, n_ip, float(ip_scale),
+                                                  out.data_ptr(), out.stride(0), batch, n_q, heads, 0.125, _stream()),
+               "decoupled_cross_attn")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ prior / embeddings
+def gemm_smallm(a, w, bias=None, residual=None, act_in=ACT_NONE, act=ACT_NONE, out=None):
+    """out[M,N] fp32 = act(act_in(a) @ w^T + bias) + residual; a fp32 [M,K], w bf16 [N,K]."""
+    lib = _lib.load()
+    _need(a, torch.float32, "a", 2)
+    _need(w, torch.bfloat16, "w", 2)
+    a = a.contiguous()
+    assert w.is_contiguous() and w.shape[1] == a.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    bias = _f32(bias, "bias")
+    if residual is not None:
+        residual = _f32(residual, "residual")
+        assert residual.shape == (M, N)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    _lib.check(lib.ia2p_gemm_smallm(a.data_ptr(), K, w.data_ptr(), _ptr(bias), _ptr(residual), N, out.data_ptr(), N, M, N, K,
+                                    act_in, act, _stream()), "gemm_smallm")
+    return out
+
+
+def causal_attn_small(qkv, batch, T, heads, out=None):
+    lib = _lib.load()
+    qkv = _f32(qkv, "qkv")
+    E = heads * 64
+    assert qkv.numel() == batch * T * 3 * E
+    if out is None:
+        out = torch.empty(batch, T, E, device=qkv.device, dtype=torch.float32)
+    _lib.check(lib.ia2p_causal_attn_small_f32(qkv.data_ptr(), out.data_ptr(), batch, T, heads, _stream()), "causal_attn_small")
+    return out

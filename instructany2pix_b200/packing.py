@@ -1,0 +1,34 @@
+"""Weight re-layout from diffusers / HF state-dict tensors to the kernel layouts (done once at load time).
+
+Pure tensor reshapes (device-agnostic torch indexing, no arithmetic on the hot path).
+"""
+from __future__ import annotations
+
+import torch
+
+
+def pack_conv3x3(w, w_shortcut=None, dtype=torch.bfloat16):
+    """Conv2d weight [Cout,Cin,3,3] (+ optional 1x1 shortcut [Cout,Csc,1,1]) -> [Cout, 9*Cin (+Csc)],
+    K order (ky, kx, cin) then shortcut channels: the tap order of ia2p_conv3x3_nhwc_bf16."""
+    cout = w.shape[0]
+    p = w.permute(0, 2, 3, 1).reshape(cout, -1)
+    if w_shortcut is not None:
+        p = torch.cat([p, w_shortcut.reshape(cout, -1)], dim=1)
+    return p.to(dtype).contiguous()
+
+
+def interleave_geglu(w, b=None, group=32):
+    """GEGLU proj weight [8C, C] (rows [0,4C) value | [4C,8C) gate) -> rows interleaved in `group`-row
+    blocks [value_0 | gate_0 | value_1 | gate_1 ...] so value/gate of one output land in the same accumulator tile."""
+    n2 = w.shape[0]
+    half = n2 // 2
+    assert half % group == 0
+    idx = torch.arange(n2, device=w.device).reshape(2, half // group, group).permute(1, 0, 2).reshape(-1)
+    wi = w[idx].contiguous()
+    bi = None if b is None else b[idx].contiguous()
+    return wi, bi
+
+
+def conv1d_to_linear(w):
+    """HF Conv1D weight [in, out] -> nn.Linear layout [out, in] (K-major rows)."""
+    return w.t().contiguous()

@@ -1,0 +1,114 @@
+"""Schedulers behind the diffusers interface the reference uses.
+
+``B200DDIMScheduler`` replaces the ``DDIMScheduler`` the app swaps in (serve.py:9; pipeline.py:105,307;
+ddim/pnp_pipeline.py:133): ``set_timesteps / timesteps / scale_model_input / step / init_noise_sigma /
+alphas_cumprod / final_alpha_cumprod / order / config / from_config``.  ``step`` is ONE kernel launch
+(x_prev = c_x x + c_e eps with host-precomputed fp64 coefficients; no device->host sync, unlike the ~8 elementwise
+launches + CPU indexing of the original), and ``cfg_step`` additionally folds the classifier-free-guidance combine and
+the duplication of the next UNet input into the same pass (custom_pipelines.py:332-357).
+``B200DDPMScheduler`` is the prior's ancestral sampler (prior/model.py:134,585,648).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import ops
+
+_DEFAULTS = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                 prediction_type="epsilon", steps_offset=1, timestep_spacing="leading", clip_sample=False,
+                 set_alpha_to_one=False)
+
+
+class _SchedulerBase:
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, **kw):
+        cfg = dict(_DEFAULTS)
+        cfg.update({k: v for k, v in kw.items() if k in _DEFAULTS})
+        if cfg["beta_schedule"] != "scaled_linear" or cfg["prediction_type"] != "epsilon" or cfg["timestep_spacing"] != "leading":
+            raise NotImplementedError(f"scheduler config outside the reference hot path: {cfg}")
+        if cfg["clip_sample"]:
+            raise NotImplementedError("clip_sample=True is not used by the reference (SDXL scheduler config)")
+        self.config = SimpleNamespace(**cfg)
+        self._cfg = cfg
+        # fp32 table exactly as diffusers builds it (kept on CPU: indexing never touches the device)
+        betas = torch.linspace(cfg["beta_start"] ** 0.5, cfg["beta_end"] ** 0.5, cfg["num_train_timesteps"], dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.one = torch.tensor(1.0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if cfg["set_alpha_to_one"] else self.alphas_cumprod[0]
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, cfg["num_train_timesteps"])[::-1].copy().astype(np.int64))
+
+    @classmethod
+    def from_config(cls, config, **kw):
+        src = config if isinstance(config, dict) else {k: getattr(config, k) for k in _DEFAULTS if hasattr(config, k)}
+        src = dict(src)
+        src.update(kw)
+        return cls(**src)
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        """``device`` is accepted for interface parity; timesteps stay on the host so the loop never syncs."""
+        self.num_inference_steps = int(num_inference_steps)
+        ratio = self._cfg["num_train_timesteps"] // self.num_inference_steps
+        ts = (np.arange(0, self.num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + self._cfg["steps_offset"]
+        self.timesteps = torch.from_numpy(ts)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def _alphas(self, timestep):
+        t = int(timestep)
+        prev = t - self._cfg["num_train_timesteps"] // self.num_inference_steps
+        return t, prev, float(self.alphas_cumprod[t])
+
+
+class B200DDIMScheduler(_SchedulerBase):
+    def coefficients(self, timestep):
+        """x_prev = c_x * x + c_e * eps (eta = 0; SURVEY A.5 fused form), computed in fp64 on the host."""
+        t, prev, a_t = self._alphas(timestep)
+        a_p = float(self.alphas_cumprod[prev]) if prev >= 0 else float(self.final_alpha_cumprod)
+        c_x = math.sqrt(a_p / a_t)
+        c_e = math.sqrt(1.0 - a_p) - math.sqrt(a_p * (1.0 - a_t) / a_t)
+        return c_x, c_e
+
+    def inverse_coefficients(self, timestep, prev_timestep):
+        """Inverse DDIM step x_t = c_x x + c_e eps (``_backward_ddim``, pnp_pipeline.py:73-85, :262-275)."""
+        a = float(self.alphas_cumprod[int(timestep)])
+        b = float(self.alphas_cumprod[int(prev_timestep)]) if prev_timestep is not None else float(self.final_alpha_cumprod)
+        return math.sqrt(a / b), math.sqrt(a) * (math.sqrt(1.0 / a - 1.0) - math.sqrt(1.0 / b - 1.0))
+
+    def step(self, model_output, timestep, sample, eta=0.0, use_clipped_model_output=False, generator=None,
+             variance_noise=None, return_dict=False):
+        if eta != 0.0:
+            raise NotImplementedError("eta != 0 is not used by the reference hot path (custom_pipelines.py:357 passes eta=0)")
+        c_x, c_e = self.coefficients(timestep)
+        prev = ops.axpby(model_output, sample, c_x, c_e)
+        return SimpleNamespace(prev_sample=prev) if return_dict else (prev,)
+
+    def cfg_step(self, eps2, timestep, sample, guidance_scale, x_in_next2=None, out=None):
+        """Fused: eps_u + g (eps_c - eps_u) -> DDIM update -> (optionally) duplicated next UNet input."""
+        c_x, c_e = self.coefficients(timestep)
+        return ops.cfg_ddim_step(eps2, sample, guidance_scale, c_x, c_e, x_out=out, x_in_next2=x_in_next2)
+
+    def inverse_step(self, model_output, timestep, prev_timestep, sample):
+        c_x, c_e = self.inverse_coefficients(timestep, prev_timestep)
+        return ops.axpby(model_output, sample, c_x, c_e)
+
+
+class B200DDPMScheduler(_SchedulerBase):
+    """DDPM ancestral step, variance_type 'fixed_small' (SURVEY A.5); used by the prior with injectable noise."""
+
+    def coefficients(self, timestep):
+        t, prev, a_t = self._alphas(timestep)
+        a_p = float(self.alphas_cumprod[prev]) if prev >= 0 else 1.0
+        cur_a = a_t / a_p
+        cur_b = 1.0 - cur_a
+        c_x0 = math.sqrt(a_p) * cur_b / (1.0 - a_t)
+        c_x = math.sqrt(cur_a) * (1.0 - a_p) / (1.0 - a_t)
+        sigma = math.sqrt(max((1.0 - a_p) / (1.0 - a_t) * cur_b, 1e-20)) if t > 0 else 0.0
+        return dict(sqrt_a=math.sqrt(a_t), sqrt_1ma=math.sqrt(1.0 - a_t), c_x0=c_x0, c_x=c_x, sigma=sigma)

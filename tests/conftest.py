@@ -20,3 +20,14 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    """Swap the C-ABI front end for the torch test double (host-logic tests on a GPU-less machine)."""
+    import instructany2pix_b200.ops as real
+    from tests import emu_ops
+    for name in dir(emu_ops):
+        if not name.startswith("_") and callable(getattr(emu_ops, name)) and hasattr(real, name):
+            monkeypatch.setattr(real, name, getattr(emu_ops, name))
+    return emu_ops

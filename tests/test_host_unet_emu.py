@@ -1,0 +1,105 @@
+"""Host-side orchestration of B200UNet / sampler checked against the oracle with the kernel test double (CPU)."""
+import torch
+
+from instructany2pix_b200.attention_processor import B200IPAttnProcessor
+from instructany2pix_b200.sampler import B200Sampler
+from instructany2pix_b200.unet import TINY_CONFIG, B200UNet
+from oracle import sampler as osampler
+from oracle.attention import ImageProjModel, IPAttnProcessor2_0, get_image_embeds
+from oracle.synth import synth_request, synth_state_dict
+from oracle.unet import TINY, OracleUNet
+
+torch.set_grad_enabled(False)
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def build_pair(with_ip=True, device="cpu"):
+    o = OracleUNet(TINY).eval()
+    o.load_state_dict(synth_state_dict(o, 0))
+    if with_ip:
+        procs = {}
+        for name, p in o.attn_processors.items():
+            if name.endswith("attn2.processor"):
+                C = dict(o.named_modules())[name[: -len(".processor")]].to_q.weight.shape[0]
+                ip = IPAttnProcessor2_0(C, TINY.cross_attention_dim, scale=0.8, num_tokens=4)
+                ip.load_state_dict(synth_state_dict({k: v.shape for k, v in ip.state_dict().items()}, 5))
+                # per-layer distinct weights
+                for k, v in ip.state_dict().items():
+                    v.copy_(synth_state_dict({name + k: v.shape}, 5)[name + k])
+                procs[name] = ip
+            else:
+                procs[name] = p
+        o.set_attn_processor(procs)
+    b = B200UNet.from_module(o, device=device)
+    return o, b
+
+
+def make_inputs(cfg, B=1, L=16):
+    reqs = [synth_request(i, cfg, L) for i in range(B)]
+    proj = ImageProjModel(cfg.cross_attention_dim, 1024, 4)
+    proj.load_state_dict(synth_state_dict(proj, 9))
+    ip, ip_u = get_image_embeds(proj, torch.stack([r["llm_embed"] for r in reqs]))
+    ctx, added = osampler.cfg_inputs(reqs, ip, ip_u)
+    lat = torch.stack([r["latent"] for r in reqs])
+    return lat, ctx, added
+
+
+def test_structure_and_plugin_api():
+    b = B200UNet(device="meta", **TINY_CONFIG)
+    o = OracleUNet(TINY)
+    assert {k: tuple(v.shape) for k, v in b.state_dict().items()} == {k: tuple(v.shape) for k, v in o.state_dict().items()}
+    assert list(b.attn_processors) == list(o.attn_processors)
+    assert b.add_embedding.linear_1.in_features == TINY.projection_class_embeddings_input_dim
+    assert b.config.time_cond_proj_dim is None and b.config.in_channels == 4
+
+
+def test_forward_matches_oracle_with_ip(emu):
+    o, b = build_pair(True)
+    lat, ctx, added = make_inputs(TINY)
+    x = torch.cat([lat, lat])
+    ref = o(x, torch.tensor(981), ctx, added_cond_kwargs=added)[0]
+    out = b(x, torch.tensor(981), ctx, added_cond_kwargs=added)[0]
+    assert out.shape == ref.shape
+    assert rel(out, ref) < 1.5e-2        # bf16 activations end to end vs fp32 oracle
+    # set_scale semantics (ip_adapter.py:211-214): mutate .scale on the processors, next forward sees it
+    for p in b.attn_processors.values():
+        if isinstance(p, B200IPAttnProcessor):
+            p.scale = 0.0
+    for p in o.attn_processors.values():
+        if isinstance(p, IPAttnProcessor2_0):
+            p.scale = 0.0
+    assert rel(b(x, 981, ctx, added_cond_kwargs=added)[0], o(x, torch.tensor(981), ctx, added_cond_kwargs=added)[0]) < 1.5e-2
+
+
+def test_forward_plain_processors_and_quirk(emu):
+    """disable(): plain processors on attn2 -> text-only attention over ALL tokens (ip_adapter.py:153-154);
+    inversion quirk: 77-token context with IP processors -> last 4 text tokens act as image tokens."""
+    o, b = build_pair(False)
+    lat, ctx, added = make_inputs(TINY)
+    x = torch.cat([lat, lat])
+    assert rel(b(x, 501, ctx, added_cond_kwargs=added)[0], o(x, torch.tensor(501), ctx, added_cond_kwargs=added)[0]) < 1.5e-2
+    o2, b2 = build_pair(True)
+    c77 = ctx[:1, :77]
+    add1 = {k: v[:1] for k, v in added.items()}
+    assert rel(b2(lat, 21, c77, added_cond_kwargs=add1)[0], o2(lat, torch.tensor(21), c77, added_cond_kwargs=add1)[0]) < 1.5e-2
+
+
+def test_sampler_generate_and_invert(emu):
+    o, b = build_pair(True)
+    lat, ctx, added = make_inputs(TINY, B=1, L=8)
+    s = B200Sampler(b, use_cuda_graph=False)
+    tr_o, tr_b = [], []
+    ref = osampler.generate(o, lat, ctx, added, num_inference_steps=4, guidance_scale=7.5, trace=tr_o)
+    out = s.generate(lat, ctx, added, num_inference_steps=4, guidance_scale=7.5, trace=tr_b,
+                     teacher=[t["x"] for t in tr_o])
+    for a, r in zip(tr_b, tr_o):
+        assert a["t"] == r["t"] and rel(a["eps2"], r["eps2"]) < 1.5e-2
+    assert rel(out, ref) < 1.5e-2
+    c1 = ctx[1:, :77]
+    add1 = {k: v[1:] for k, v in added.items()}
+    ref_i = osampler.invert(o, lat, c1, add1, num_inference_steps=3)
+    out_i = s.invert(lat, c1, add1, num_inference_steps=3)
+    assert rel(out_i, ref_i) < 1.5e-2

@@ -1,0 +1,252 @@
+"""GPU unit tests of every C-ABI kernel against a plain torch fp32 reference of the same op (tolerances stated inline)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from instructany2pix_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+# references must be true fp32 (cuDNN/cuBLAS default to TF32 for fp32 inputs)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def rnd(*shape, scale=1.0, dtype=torch.bfloat16, seed=None):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(hash(shape) % (2 ** 31) if seed is None else seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+# bf16 output rounding is 2^-9 relative per element; accumulation is fp32 -> rel-L2 of a correct kernel ~2e-3
+TOL = 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (128, 320, 64), (1000, 640, 1280), (154, 2560, 2048),
+                                   (4096, 1280, 640), (512, 64, 192), (300, 1920, 640)])
+def test_gemm_plain(M, N, K):
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    out = ops.gemm(a, w)
+    assert rel(out, a.float() @ w.float().t()) < TOL
+
+
+def test_gemm_epilogues():
+    M, N, K = 768, 640, 320
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias = rnd(N, dtype=torch.float32)
+    rowbias = rnd(3, N, dtype=torch.float32)
+    res = rnd(M, N)
+    ref = a.float() @ w.float().t() + bias + rowbias.repeat_interleave(256, 0) + res.float()
+    out = ops.gemm(a, w, bias=bias, rowbias=rowbias, rows_per_batch=256, residual=res)
+    assert rel(out, ref) < TOL
+
+
+def test_gemm_fp32_stream():
+    """residual-stream variant: fp32 residual in, fp32 out (only tensor-core operands are bf16)."""
+    M, N, K = 512, 1280, 640
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias, res = rnd(N, dtype=torch.float32), rnd(M, N, dtype=torch.float32)
+    out = ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32)
+    assert out.dtype == torch.float32
+    assert rel(out, a.float() @ w.float().t() + bias + res) < 2e-6
+    out2 = ops.gemm(a, w, residual=res)          # fp32 residual, bf16 out
+    assert out2.dtype == torch.bfloat16 and rel(out2, a.float() @ w.float().t() + res) < TOL
+
+
+def test_gemm_k_concat_and_strided_views():
+    M, K1, K2, N = 640, 128, 192, 320
+    big = rnd(M, 512)
+    a, a2 = big[:, :K1], big[:, 256:256 + K2]          # row-strided views
+    w = rnd(N, K1 + K2, scale=(K1 + K2) ** -0.5)
+    outbuf = torch.zeros(M, 2 * N, device=DEV, dtype=torch.bfloat16)
+    out = ops.gemm(a, w, a2=a2, out=outbuf[:, N:])
+    ref = torch.cat([a, a2], 1).float() @ w.float().t()
+    assert rel(out, ref) < TOL
+    assert outbuf[:, :N].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("M,C", [(512, 128), (1000, 640)])
+def test_gemm_geglu(M, C):
+    a = rnd(M, C)
+    w = rnd(8 * C, C, scale=C ** -0.5)           # diffusers layout: rows [0,4C) value, [4C,8C) gate
+    b = rnd(8 * C, dtype=torch.float32, scale=0.1)
+    from instructany2pix_b200.packing import interleave_geglu
+    wi, bi = interleave_geglu(w, b)
+    out = ops.gemm(a, wi, bias=bi, geglu=True)
+    h = a.float() @ w.float().t() + b
+    ref = h[:, :4 * C] * F.gelu(h[:, 4 * C:])
+    assert out.shape == (M, 4 * C)
+    assert rel(out, ref) < TOL
+
+
+def _conv_ref(x, w, stride=1):
+    return F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=stride, padding=1).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 16, 64, 64, 1), (1, 32, 32, 128, 160, 1), (3, 8, 8, 64, 128, 1),
+                                                   (2, 64, 64, 64, 320, 1), (2, 32, 32, 128, 128, 2), (1, 16, 16, 64, 64, 2),
+                                                   (2, 128, 128, 64, 64, 1), (5, 4, 4, 64, 32, 1), (1, 24, 48, 64, 64, 1)])
+def test_conv3x3(B, H, W, Cin, Cout, stride):
+    from instructany2pix_b200.packing import pack_conv3x3
+    x = rnd(B, H, W, Cin)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    out = ops.conv3x3(x, pack_conv3x3(w), Cout, stride=stride)
+    assert rel(out, _conv_ref(x, w, stride)) < TOL
+
+
+def test_conv3x3_fused_shortcut_bias_temb_residual():
+    from instructany2pix_b200.packing import pack_conv3x3
+    B, H, W, Cin, Cout, Ca, Cb = 2, 16, 16, 128, 64, 64, 128
+    x = rnd(B, H, W, Cin)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    sa, sb = rnd(B, H, W, Ca), rnd(B, H, W, Cb)
+    wsc = rnd(Cout, Ca + Cb, 1, 1, scale=(Ca + Cb) ** -0.5)
+    bias = rnd(Cout, dtype=torch.float32)
+    temb = rnd(B, Cout, dtype=torch.float32)
+    res = rnd(B, H, W, Cout)
+    out = ops.conv3x3(x, pack_conv3x3(w, wsc), Cout, sc_a=sa, sc_b=sb, bias=bias, rowbias=temb, residual=res)
+    ref = _conv_ref(x, w) + torch.cat([sa, sb], -1).float() @ wsc.float().reshape(Cout, -1).t() + bias \
+        + temb[:, None, None, :] + res.float()
+    assert rel(out, ref) < TOL
+    out32 = ops.conv3x3(x, pack_conv3x3(w, wsc), Cout, sc_a=sa, sc_b=sb, bias=bias, rowbias=temb, residual=res.float(),
+                        out_dtype=torch.float32)
+    assert out32.dtype == torch.float32 and rel(out32, ref) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,HW,Ca,Cb,silu", [(2, 256, 64, 0, True), (2, 1024, 320, 0, True), (3, 64, 640, 320, True),
+                                             (1, 4096, 1280, 0, False), (2, 100, 1280, 1280, True)])
+def test_groupnorm(B, HW, Ca, Cb, silu, dtype):
+    xa = (rnd(B, HW, Ca, scale=2.0, dtype=torch.float32) + 0.5).to(dtype)
+    xb = rnd(B, HW, Cb, dtype=dtype) if Cb else None
+    C = Ca + Cb
+    gamma, beta = rnd(C, dtype=torch.float32) + 1.0, rnd(C, dtype=torch.float32)
+    out, raw = ops.groupnorm(xa, xb, gamma, beta, 32, 1e-5, silu, want_raw=True)
+    x = xa if xb is None else torch.cat([xa, xb], -1)
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    assert out.dtype == torch.bfloat16 and rel(out, ref) < TOL
+    assert torch.equal(raw, x.to(torch.bfloat16))
+    assert torch.equal(ops.groupnorm(xa, xb, gamma, beta, 32, 1e-5, silu), out)
+
+
+@pytest.mark.parametrize("rows,cols,dtype,odt", [(1000, 640, torch.bfloat16, torch.bfloat16), (512, 1280, torch.float32, torch.bfloat16),
+                                                 (28, 1024, torch.float32, torch.float32), (7, 64, torch.bfloat16, torch.bfloat16),
+                                                 (4, 2048, torch.float32, torch.float32), (300, 640, torch.float32, torch.bfloat16)])
+def test_layernorm(rows, cols, dtype, odt):
+    x = rnd(rows, cols, dtype=dtype, scale=1.5) + 0.3
+    gamma, beta = rnd(cols, dtype=torch.float32) + 1.0, rnd(cols, dtype=torch.float32)
+    out = ops.layernorm(x, gamma, beta, 1e-5, out_dtype=odt)
+    ref = F.layer_norm(x.float(), (cols,), gamma, beta, 1e-5)
+    assert out.dtype == odt and rel(out, ref) < (TOL if odt == torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.parametrize("B,N,heads", [(2, 256, 2), (1, 1024, 10), (2, 200, 1), (1, 64, 4), (1, 4096, 2)])
+def test_flash_self_attn(B, N, heads):
+    C = heads * 64
+    qkv = rnd(B * N, 3 * C)
+    out = ops.flash_self_attn(qkv, B, N, heads)
+    q, k, v = [t.float().reshape(B, N, heads, 64).transpose(1, 2) for t in qkv.split(C, dim=1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, C)
+    assert rel(out, ref) < 6e-3        # P is rounded to bf16 before P.V (as in flash-attention): ~2^-9 extra
+
+
+@pytest.mark.parametrize("n_text,n_ip,scale", [(77, 4, 1.0), (73, 4, 0.6), (81, 0, 1.0), (77, 4, 0.0), (120, 16, 0.5)])
+def test_decoupled_cross_attn(n_text, n_ip, scale):
+    B, N, heads = 2, 300, 3
+    C = heads * 64
+    q = rnd(B * N, C)
+    kvt = rnd(B * n_text, 2 * C)
+    kvi = rnd(B * n_ip, 2 * C) if n_ip else None
+    out = ops.cross_attn(q, kvt, n_text, kvi, n_ip, scale, B, N, heads)
+    hq = q.float().reshape(B, N, heads, 64).transpose(1, 2)
+    sp = lambda t, n: t.float().reshape(B, n, heads, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(hq, sp(kvt[:, :C], n_text), sp(kvt[:, C:], n_text))
+    if n_ip:
+        ref = ref + scale * F.scaled_dot_product_attention(hq, sp(kvi[:, :C], n_ip), sp(kvi[:, C:], n_ip))
+    assert rel(out, ref.transpose(1, 2).reshape(B * N, C)) < 6e-3
+
+
+def test_cfg_ddim_and_axpby():
+    B, n = 3, 4 * 32 * 32
+    for dt in (torch.float32, torch.bfloat16, torch.float16):
+        eps2, x = rnd(2 * B, n, dtype=dt), rnd(B, n, dtype=dt)
+        nxt = torch.empty(2 * B, n, device=DEV, dtype=dt)
+        out = ops.cfg_ddim_step(eps2, x, 7.5, 1.01, -0.05, x_in_next2=nxt)
+        eu, ec = eps2.float().chunk(2)
+        ref = 1.01 * x.float() + (-0.05) * (eu + 7.5 * (ec - eu))
+        tol = 1e-6 if dt == torch.float32 else 5e-3
+        assert rel(out, ref) < tol and rel(nxt, torch.cat([ref, ref])) < tol
+        assert rel(ops.axpby(eps2[:B], x, 0.9, 0.2), 0.9 * x.float() + 0.2 * eps2[:B].float()) < tol
+
+
+def test_prior_step_and_timestep_embedding():
+    n = 1024
+    x0, x, noise = rnd(2, n, dtype=torch.float32), rnd(n, dtype=torch.float32), rnd(n, dtype=torch.float32)
+    sa, s1 = 0.8, 0.6
+    out = ops.prior_cfg_ddpm_step(x0, x, noise, sa, s1, 10.0, 0.3, 0.7, 0.05)
+    ec, eu = (x - sa * x0[0]) / s1, (x - sa * x0[1]) / s1
+    e = eu + 10.0 * (ec - eu)
+    ref = 0.3 * (x - s1 * e) / sa + 0.7 * x + 0.05 * noise
+    assert rel(out, ref) < 1e-5
+    t = torch.tensor([981.0, 1.0, 6.5], device=DEV)
+    emb = ops.timestep_embedding(t, 320, True, 0.0)
+    half = 160
+    f = torch.exp(-math.log(10000) * torch.arange(half, device=DEV, dtype=torch.float32) / half)
+    a = t[:, None] * f[None]
+    assert rel(emb, torch.cat([a.cos(), a.sin()], -1)) < 2e-4     # fast sin/cos at arguments up to ~1e3
+
+
+def test_upsample_conv_in_out():
+    x = rnd(2, 8, 8, 64)
+    up = ops.upsample2x(x)
+    assert torch.equal(up, x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    x32 = rnd(2, 8, 8, 64, dtype=torch.float32)
+    assert torch.equal(ops.upsample2x(x32), x32.to(torch.bfloat16).repeat_interleave(2, 1).repeat_interleave(2, 2))
+    assert torch.equal(ops.to_bf16(x32), x32.to(torch.bfloat16))
+    lat = rnd(1, 4, 16, 16, dtype=torch.float32)
+    w, b = rnd(64, 4, 3, 3, dtype=torch.float32, scale=0.2), rnd(64, dtype=torch.float32)
+    y = ops.conv_in(lat, w, b, out_batch=2)
+    ref = F.conv2d(lat, w, b, padding=1).permute(0, 2, 3, 1)
+    assert rel(y[0], ref[0]) < TOL and torch.equal(y[0], y[1])
+    y32 = ops.conv_in(lat, w, b, out_batch=2, out_dtype=torch.float32)
+    assert y32.dtype == torch.float32 and rel(y32[1], ref[0]) < 1e-5
+    h = rnd(2, 16, 16, 64)
+    wo, bo = rnd(4, 64, 3, 3, dtype=torch.float32, scale=0.05), rnd(4, dtype=torch.float32)
+    z = ops.conv_out(h, wo.permute(0, 2, 3, 1).contiguous(), bo)
+    assert rel(z, F.conv2d(h.float().permute(0, 3, 1, 2), wo, bo, padding=1)) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,act_in,act", [(22, 3072, 1024, 0, 0), (28, 1024, 4096, 0, 1), (2, 1280, 320, 2, 0),
+                                              (70, 1024, 512, 0, 2), (16, 8, 32, 0, 0)])
+def test_gemm_smallm(M, N, K, act_in, act):
+    a = rnd(M, K, dtype=torch.float32)
+    w = rnd(N, K, scale=K ** -0.5)
+    bias, res = rnd(N, dtype=torch.float32), rnd(M, N, dtype=torch.float32)
+    out = ops.gemm_smallm(a, w, bias=bias, residual=res, act_in=act_in, act=act)
+    ai = F.silu(a) if act_in == 2 else a
+    h = ai @ w.float().t() + bias
+    if act == 1:
+        h = 0.5 * h * (1 + torch.tanh(math.sqrt(2 / math.pi) * (h + 0.044715 * h ** 3)))
+    elif act == 2:
+        h = F.silu(h)
+    assert rel(out, h + res) < 2e-5      # hi/lo bf16 split of the fp32 activations: ~2^-16 relative
+
+
+def test_causal_attn_small():
+    B, T, heads = 2, 14, 16
+    E = heads * 64
+    qkv = rnd(B, T, 3 * E, dtype=torch.float32)
+    out = ops.causal_attn_small(qkv, B, T, heads)
+    q, k, v = [t.reshape(B, T, heads, 64).transpose(1, 2) for t in qkv.split(E, dim=2)]
+    ref = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, T, E)
+    assert rel(out, ref) < 1e-5
