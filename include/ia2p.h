@@ -71,7 +71,8 @@ int ia2p_cast_to_bf16(const void* x, int x_dtype, void* y, int64_t n, void* stre
  * Replaces [3P] ResnetBlock2D norm1/norm2 + SiLU, torch.cat([h, skip], 1), Transformer2DModel.norm, conv_norm_out.
  * xa: [batch, hw, ca], xb: [batch, hw, cb] or NULL, both x_dtype (fp32|bf16); y: [batch, hw, ca+cb] bf16;
  * raw (nullable): [batch, hw, ca+cb] bf16 receives the un-normalised concat (operand of the fused 1x1 shortcut conv).
- * workspace: batch*groups*2 doubles (zeroed by the call).  (ca+cb) % groups == 0, ca % 8 == cb % 8 == 0. */
+ * workspace: ia2p_groupnorm_workspace_bytes() of scratch (per-slab partial sums; results are bit-reproducible:
+ * no atomics).  (ca+cb) % groups == 0, ca % 8 == cb % 8 == 0, ca+cb <= 4096. */
 int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, int64_t cb, int x_dtype,
                         const float* gamma, const float* beta, void* y, void* raw,
                         int64_t batch, int64_t hw, int groups, float eps, int silu,

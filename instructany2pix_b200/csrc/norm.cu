@@ -35,21 +35,21 @@ template <> struct Vec8<float> {
 
 // ---------------------------------------------------------------- GroupNorm statistics
 // grid (slabs, batch); block (CV = C/8 vector lanes, ROWS pixel lanes).  Every thread owns one 8-channel vector
-// column and strides over the slab's pixels; per-channel partials are folded across ROWS in shared memory, then
-// per-group sums go to global fp64 atomics.
+// column and strides over the slab's pixels.  Deterministic by construction (no atomics): per-thread partials go to
+// shared memory, one thread per group folds them in a fixed order, and the per-slab results are written to
+// partials[b][slab][group] which the apply kernel sums in slab order.
+constexpr int kGnMaxSlabs = 128;
+
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
-                                long long hw, int groups, int pix_per_slab, double* __restrict__ stats) {
-  extern __shared__ float sm[];   // [2][C]
+                                long long hw, int groups, int pix_per_slab, double* __restrict__ partials) {
+  extern __shared__ float sm[];   // [ROWS][2][C]
   const int C = ca + cb;
-  const int cv = threadIdx.x;     // vector index within the pixel
-  const int c0 = cv * 8;
+  const int c0 = threadIdx.x * 8;
   const long long b = blockIdx.y;
   const long long p_begin = (long long)blockIdx.x * pix_per_slab;
   long long p_end = p_begin + pix_per_slab;
   if (p_end > hw) p_end = hw;
-  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) sm[i] = 0.f;
-  __syncthreads();
 
   float s[8], ss[8];
 #pragma unroll
@@ -63,18 +63,20 @@ __global__ void gn_stats_kernel(const T* __restrict__ xa, int ca, const T* __res
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
   }
+  float* mine = sm + (size_t)threadIdx.y * 2 * C;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[c0 + j], s[j]);
-    atomicAdd(&sm[C + c0 + j], ss[j]);
-  }
+  for (int j = 0; j < 8; ++j) { mine[c0 + j] = s[j]; mine[C + c0 + j] = ss[j]; }
   __syncthreads();
   const int cpg = C / groups;
   for (int g = threadIdx.y * blockDim.x + threadIdx.x; g < groups; g += blockDim.x * blockDim.y) {
     double a = 0.0, q = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += (double)sm[c]; q += (double)sm[C + c]; }
-    atomicAdd(&stats[(b * groups + g) * 2 + 0], a);
-    atomicAdd(&stats[(b * groups + g) * 2 + 1], q);
+    for (int r = 0; r < (int)blockDim.y; ++r) {
+      const float* row = sm + (size_t)r * 2 * C;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += (double)row[c]; q += (double)row[C + c]; }
+    }
+    double* dst = partials + ((b * gridDim.x + blockIdx.x) * groups + g) * 2;
+    dst[0] = a;
+    dst[1] = q;
   }
 }
 
@@ -83,23 +85,35 @@ template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw, long long hw, int groups,
-                                float eps, int silu, int pix_per_slab, const double* __restrict__ stats) {
-  extern __shared__ float sm[];   // scale[C], shift[C]
+                                float eps, int silu, int pix_per_slab, const double* __restrict__ partials) {
+  extern __shared__ float sm[];   // scale[C], shift[C], then mean[groups], rstd[groups]
   const int C = ca + cb;
   const int cpg = C / groups;
   const long long b = blockIdx.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthr = blockDim.x * blockDim.y;
   const double cnt = (double)hw * cpg;
+  float* gmean = sm + 2 * C;
+  float* grstd = gmean + groups;
+  for (int g = tid; g < groups; g += nthr) {
+    double a = 0.0, q = 0.0;
+    for (int sl = 0; sl < (int)gridDim.x; ++sl) {        // fixed slab order: bit-reproducible
+      const double* src = partials + ((b * gridDim.x + sl) * groups + g) * 2;
+      a += src[0];
+      q += src[1];
+    }
+    const double mean = a / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gmean[g] = (float)mean;
+    grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
   for (int c = tid; c < C; c += nthr) {
     const int g = c / cpg;
-    const double mean = stats[(b * groups + g) * 2] / cnt;
-    double var = stats[(b * groups + g) * 2 + 1] / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = rstd * gamma[c];
+    const float sc = grstd[g] * gamma[c];
     sm[c] = sc;
-    sm[C + c] = beta[c] - (float)mean * sc;
+    sm[C + c] = beta[c] - gmean[g] * sc;
   }
   __syncthreads();
   const int c0 = threadIdx.x * 8;
@@ -189,7 +203,9 @@ static int launch_ln(const void* x, const float* gamma, const float* beta, void*
 
 using namespace ia2p;
 
-extern "C" int64_t ia2p_groupnorm_workspace_bytes(int64_t batch, int groups) { return batch * groups * 2 * (int64_t)sizeof(double); }
+extern "C" int64_t ia2p_groupnorm_workspace_bytes(int64_t batch, int groups) {
+  return batch * kGnMaxSlabs * groups * 2 * (int64_t)sizeof(double);
+}
 
 extern "C" int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, int64_t cb, int x_dtype, const float* gamma,
                                    const float* beta, void* y, void* raw, int64_t batch, int64_t hw, int groups, float eps,
@@ -200,7 +216,7 @@ extern "C" int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, i
   IA2P_REQUIRE((xb == nullptr) == (cb == 0), IA2P_E_ARG, "groupnorm: xb and cb must be given together");
   const int64_t C = ca + cb;
   IA2P_REQUIRE(ca % 8 == 0 && cb % 8 == 0 && C % groups == 0, IA2P_E_SHAPE, "groupnorm: ca=%lld cb=%lld groups=%d unsupported", (long long)ca, (long long)cb, groups);
-  IA2P_REQUIRE(C / 8 <= 1024 && C * 8 <= 48 * 1024, IA2P_E_SHAPE, "groupnorm: C=%lld too large", (long long)C);
+  IA2P_REQUIRE(C / 8 <= 1024 && C <= 4096 && groups <= 64, IA2P_E_SHAPE, "groupnorm: C=%lld / groups=%d too large", (long long)C, groups);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int cv = (int)(C / 8);
   int rows = 512 / cv;
@@ -210,23 +226,24 @@ extern "C" int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, i
   long long slabs = ((long long)sm_count() * 4 + batch - 1) / batch;
   long long max_slabs = (hw + rows * 4 - 1) / (rows * 4);
   if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs > kGnMaxSlabs) slabs = kGnMaxSlabs;
   if (slabs < 1) slabs = 1;
   const int pps = (int)((hw + slabs - 1) / slabs);
   slabs = (hw + pps - 1) / pps;
   const dim3 block(cv, rows), grid((unsigned)slabs, (unsigned)batch);
-  const size_t smem = 2 * C * sizeof(float);
+  const size_t smem_stats = (size_t)rows * 2 * C * sizeof(float);           // <= 32 KB (rows * C <= 4096)
+  const size_t smem = (2 * C + 2 * groups) * sizeof(float);
   double* stats = static_cast<double*>(workspace);
-  IA2P_CUDA(cudaMemsetAsync(stats, 0, (size_t)ia2p_groupnorm_workspace_bytes(batch, groups), st));
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   __nv_bfloat16* rp = static_cast<__nv_bfloat16*>(raw);
   if (x_dtype == IA2P_BF16) {
     const __nv_bfloat16 *a = static_cast<const __nv_bfloat16*>(xa), *b = static_cast<const __nv_bfloat16*>(xb);
-    gn_stats_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, hw, groups, pps, stats);
+    gn_stats_kernel<<<grid, block, smem_stats, st>>>(a, (int)ca, b, (int)cb, hw, groups, pps, stats);
     IA2P_LAUNCH_CHECK();
     gn_apply_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
   } else {
     const float *a = static_cast<const float*>(xa), *b = static_cast<const float*>(xb);
-    gn_stats_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, hw, groups, pps, stats);
+    gn_stats_kernel<<<grid, block, smem_stats, st>>>(a, (int)ca, b, (int)cb, hw, groups, pps, stats);
     IA2P_LAUNCH_CHECK();
     gn_apply_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
   }

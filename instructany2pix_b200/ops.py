@@ -18,6 +18,31 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernel-launch accounting (bench.py's "gpu_launches") and optional per-call CUDA-event profiling (bench.py's roofline):
+# PROFILE, when a list, receives (symbol, flops, start_event, end_event) for every C-ABI call made in eager mode.
+LAUNCHES = 0
+PROFILE = None
+_KERNELS_PER_CALL = {"ia2p_groupnorm_nhwc": 2}
+_FLOPS = 0.0
+
+
+def _run(fn, args, what):
+    global LAUNCHES, _FLOPS
+    LAUNCHES += _KERNELS_PER_CALL.get(fn.__name__, 1)
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status = fn(*args)
+        e1.record()
+        prof.append((fn.__name__, _FLOPS, e0, e1))
+    else:
+        status = fn(*args)
+    _FLOPS = 0.0
+    if status != 0:
+        _lib.check(status, what)
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -58,7 +83,7 @@ def cfg_ddim_step(eps2, x, g, c_x, c_e, x_out=None, x_in_next2=None):
     assert eps2.numel() == 2 * x.numel()
     if x_out is None:
         x_out = torch.empty_like(x)
-    _lib.check(lib.ia2p_cfg_ddim_step(eps2.data_ptr(), _DT[eps2.dtype], x.data_ptr(), x_out.data_ptr(), _DT[x.dtype],
+    _run(lib.ia2p_cfg_ddim_step, (eps2.data_ptr(), _DT[eps2.dtype], x.data_ptr(), x_out.data_ptr(), _DT[x.dtype],
                                       _ptr(x_in_next2), _DT[x_in_next2.dtype] if x_in_next2 is not None else F32,
                                       batch, n, float(g), float(c_x), float(c_e), _stream()), "cfg_ddim_step")
     return x_out
@@ -70,7 +95,7 @@ def axpby(eps, x, c_x, c_e, out=None):
     eps, x = eps.contiguous(), x.contiguous()
     if out is None:
         out = torch.empty_like(x)
-    _lib.check(lib.ia2p_axpby(eps.data_ptr(), _DT[eps.dtype], x.data_ptr(), out.data_ptr(), _DT[x.dtype], x.numel(),
+    _run(lib.ia2p_axpby, (eps.data_ptr(), _DT[eps.dtype], x.data_ptr(), out.data_ptr(), _DT[x.dtype], x.numel(),
                               float(c_x), float(c_e), _stream()), "axpby")
     return out
 
@@ -83,7 +108,7 @@ def prior_cfg_ddpm_step(x0_pair, x, noise, sqrt_a, sqrt_1ma, g, c_x0, c_x, sigma
     assert x0_pair.numel() == 2 * n
     if out is None:
         out = torch.empty_like(x)
-    _lib.check(lib.ia2p_prior_cfg_ddpm_step(x0_pair.data_ptr(), x.data_ptr(), _ptr(noise), out.data_ptr(), n, float(sqrt_a),
+    _run(lib.ia2p_prior_cfg_ddpm_step, (x0_pair.data_ptr(), x.data_ptr(), _ptr(noise), out.data_ptr(), n, float(sqrt_a),
                                             float(sqrt_1ma), float(g), float(c_x0), float(c_x), float(sigma), _stream()),
                "prior_cfg_ddpm_step")
     return out
@@ -93,7 +118,7 @@ def timestep_embedding(t, dim, flip_sin_to_cos=True, shift=0.0, dtype=torch.floa
     lib = _lib.load()
     t = _f32(t.reshape(-1), "t")
     out = torch.empty(t.numel(), dim, device=t.device, dtype=dtype)
-    _lib.check(lib.ia2p_timestep_embedding(t.data_ptr(), t.numel(), dim, int(flip_sin_to_cos), float(shift), out.data_ptr(),
+    _run(lib.ia2p_timestep_embedding, (t.data_ptr(), t.numel(), dim, int(flip_sin_to_cos), float(shift), out.data_ptr(),
                                            _DT[dtype], _stream()), "timestep_embedding")
     return out
 
@@ -106,7 +131,7 @@ def to_bf16(x):
     require_cuda(x, "to_bf16")
     x = x.contiguous()
     y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    _lib.check(lib.ia2p_cast_to_bf16(x.data_ptr(), _DT[x.dtype], y.data_ptr(), x.numel(), _stream()), "cast_to_bf16")
+    _run(lib.ia2p_cast_to_bf16, (x.data_ptr(), _DT[x.dtype], y.data_ptr(), x.numel(), _stream()), "cast_to_bf16")
     return y
 
 
@@ -118,7 +143,7 @@ def upsample2x(x):
     x = x.contiguous()
     b, h, w, c = x.shape
     y = torch.empty(b, 2 * h, 2 * w, c, device=x.device, dtype=torch.bfloat16)
-    _lib.check(lib.ia2p_upsample2x_nhwc(x.data_ptr(), _DT[x.dtype], y.data_ptr(), b, h, w, c, _stream()), "upsample2x")
+    _run(lib.ia2p_upsample2x_nhwc, (x.data_ptr(), _DT[x.dtype], y.data_ptr(), b, h, w, c, _stream()), "upsample2x")
     return y
 
 
@@ -150,7 +175,7 @@ def groupnorm(xa, xb, gamma, beta, groups, eps, silu, want_raw=False):
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 4096), device=xa.device, dtype=torch.uint8)
         _GN_WS[key] = ws
-    _lib.check(lib.ia2p_groupnorm_nhwc(xa.data_ptr(), ca, _ptr(xb), cb, _DT[xa.dtype], gamma.data_ptr(), beta.data_ptr(),
+    _run(lib.ia2p_groupnorm_nhwc, (xa.data_ptr(), ca, _ptr(xb), cb, _DT[xa.dtype], gamma.data_ptr(), beta.data_ptr(),
                                        out.data_ptr(), _ptr(raw), b, hw, groups, float(eps), int(silu), ws.data_ptr(),
                                        _stream()), "groupnorm")
     return (out, raw) if want_raw else out
@@ -168,7 +193,7 @@ def layernorm(x, gamma, beta, eps, out_dtype=None):
     rows = x.numel() // cols
     gamma, beta = _f32(gamma, "gamma"), _f32(beta, "beta")
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    _lib.check(lib.ia2p_layernorm(x.data_ptr(), _DT[x.dtype], gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+    _run(lib.ia2p_layernorm, (x.data_ptr(), _DT[x.dtype], gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
                                   _DT[out_dtype], rows, cols, float(eps), _stream()), "layernorm")
     return out
 
@@ -204,7 +229,9 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
         assert residual.shape == (M, n_out) and residual.dtype in (torch.bfloat16, torch.float32)
         ldr, res_dt = _rows(residual, "residual"), _DT[residual.dtype]
     bias, rowbias = _f32(bias, "bias"), _f32(rowbias, "rowbias")
-    _lib.check(lib.ia2p_gemm_bf16(a.data_ptr(), lda, K1, _ptr(a2), lda2, K2, w.data_ptr(), out.data_ptr(), ldo, M, N,
+    global _FLOPS
+    _FLOPS = 2.0 * M * N * (K1 + K2)
+    _run(lib.ia2p_gemm_bf16, (a.data_ptr(), lda, K1, _ptr(a2), lda2, K2, w.data_ptr(), out.data_ptr(), ldo, M, N,
                                   _ptr(bias), _ptr(rowbias), int(rows_per_batch), _ptr(residual), ldr, res_dt,
                                   _DT[out.dtype], _lib.EPI_GEGLU if geglu else _lib.EPI_NONE, _stream()), "gemm_bf16")
     return out
@@ -236,7 +263,9 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
         assert residual.shape == out.shape and residual.dtype in (torch.bfloat16, torch.float32)
         res_dt = _DT[residual.dtype]
     bias, rowbias = _f32(bias, "bias"), _f32(rowbias, "rowbias")
-    _lib.check(lib.ia2p_conv3x3_nhwc_bf16(x.data_ptr(), B, H, W, Cin, stride, w.data_ptr(), _ptr(sc_a), ca, _ptr(sc_b), cb,
+    global _FLOPS
+    _FLOPS = 2.0 * B * Ho * Wo * cout * w.shape[1]
+    _run(lib.ia2p_conv3x3_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, stride, w.data_ptr(), _ptr(sc_a), ca, _ptr(sc_b), cb,
                                           out.data_ptr(), _DT[out_dtype], cout, _ptr(bias), _ptr(rowbias), _ptr(residual),
                                           res_dt, _stream()), "conv3x3")
     return out
@@ -253,7 +282,7 @@ def conv_in(x_nchw, w, bias, out_batch=None, out_dtype=torch.bfloat16):
     w, bias = _f32(w, "w"), _f32(bias, "bias")
     cout = w.shape[0]
     out = torch.empty(B, H, W, cout, device=x_nchw.device, dtype=out_dtype)
-    _lib.check(lib.ia2p_conv_in_nchw(x_nchw.data_ptr(), _DT[x_nchw.dtype], in_b, B, H, W, cin, w.data_ptr(), _ptr(bias),
+    _run(lib.ia2p_conv_in_nchw, (x_nchw.data_ptr(), _DT[x_nchw.dtype], in_b, B, H, W, cin, w.data_ptr(), _ptr(bias),
                                      out.data_ptr(), _DT[out_dtype], cout, _stream()), "conv_in")
     return out
 
@@ -267,7 +296,7 @@ def conv_out(x, w, bias, out_dtype=torch.float32):
     w, bias = _f32(w, "w"), _f32(bias, "bias")
     cout = w.shape[0]
     out = torch.empty(B, cout, H, W, device=x.device, dtype=out_dtype)
-    _lib.check(lib.ia2p_conv_out_nhwc(x.data_ptr(), B, H, W, Cin, w.data_ptr(), _ptr(bias), out.data_ptr(), _DT[out_dtype],
+    _run(lib.ia2p_conv_out_nhwc, (x.data_ptr(), B, H, W, Cin, w.data_ptr(), _ptr(bias), out.data_ptr(), _DT[out_dtype],
                                       cout, _stream()), "conv_out")
     return out
 
@@ -283,7 +312,9 @@ def flash_self_attn(qkv, batch, n_tokens, heads, out=None):
     if out is None:
         out = torch.empty(batch * n_tokens, C, device=qkv.device, dtype=torch.bfloat16)
     es = qkv.element_size()
-    _lib.check(lib.ia2p_flash_self_attn_bf16(qkv.data_ptr(), qkv.data_ptr() + C * es, qkv.data_ptr() + 2 * C * es, ld,
+    global _FLOPS
+    _FLOPS = 4.0 * batch * heads * n_tokens * n_tokens * 64
+    _run(lib.ia2p_flash_self_attn_bf16, (qkv.data_ptr(), qkv.data_ptr() + C * es, qkv.data_ptr() + 2 * C * es, ld,
                                              out.data_ptr(), out.stride(0), batch, n_tokens, heads, 0.125, _stream()),
                "flash_self_attn")
     return out
@@ -305,7 +336,9 @@ def cross_attn(q, kv_text, n_text, kv_ip, n_ip, ip_scale, batch, n_q, heads, out
         kip, vip, ldip = 0, 0, 0
     if out is None:
         out = torch.empty(batch * n_q, C, device=q.device, dtype=torch.bfloat16)
-    _lib.check(lib.ia2p_decoupled_cross_attn_bf16(q.data_ptr(), q.stride(0), kv_text.data_ptr(), kv_text.data_ptr() + C * es,
+    global _FLOPS
+    _FLOPS = 4.0 * batch * heads * n_q * (n_text + n_ip) * 64
+    _run(lib.ia2p_decoupled_cross_attn_bf16, (q.data_ptr(), q.stride(0), kv_text.data_ptr(), kv_text.data_ptr() + C * es,
                                                   kv_text.stride(0), n_text, kip, vip, ldip, n_ip, float(ip_scale),
                                                   out.data_ptr(), out.stride(0), batch, n_q, heads, 0.125, _stream()),
                "decoupled_cross_attn")
@@ -328,7 +361,7 @@ def gemm_smallm(a, w, bias=None, residual=None, act_in=ACT_NONE, act=ACT_NONE, o
         assert residual.shape == (M, N)
     if out is None:
         out = torch.empty(M, N, device=a.device, dtype=torch.float32)
-    _lib.check(lib.ia2p_gemm_smallm(a.data_ptr(), K, w.data_ptr(), _ptr(bias), _ptr(residual), N, out.data_ptr(), N, M, N, K,
+    _run(lib.ia2p_gemm_smallm, (a.data_ptr(), K, w.data_ptr(), _ptr(bias), _ptr(residual), N, out.data_ptr(), N, M, N, K,
                                     act_in, act, _stream()), "gemm_smallm")
     return out
 
@@ -340,5 +373,5 @@ def causal_attn_small(qkv, batch, T, heads, out=None):
     assert qkv.numel() == batch * T * 3 * E
     if out is None:
         out = torch.empty(batch, T, E, device=qkv.device, dtype=torch.float32)
-    _lib.check(lib.ia2p_causal_attn_small_f32(qkv.data_ptr(), out.data_ptr(), batch, T, heads, _stream()), "causal_attn_small")
+    _run(lib.ia2p_causal_attn_small_f32, (qkv.data_ptr(), out.data_ptr(), batch, T, heads, _stream()), "causal_attn_small")
     return out

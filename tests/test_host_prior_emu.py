@@ -1,0 +1,69 @@
+"""B200Prior host logic vs the oracle (and, through golden fixtures, vs the reference code) with the kernel test double."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from instructany2pix_b200.prior import B200Prior
+from oracle import gen_golden as G
+from oracle.prior import OraclePrior
+from oracle.synth import synth_state_dict
+
+torch.set_grad_enabled(False)
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "prior.npz")
+
+
+def cos(a, b):
+    return torch.nn.functional.cosine_similarity(a.flatten().float(), b.flatten().float(), dim=0).item()
+
+
+def build(n_layer, device="cpu", graph=False):
+    o = OraclePrior(n_layer=n_layer).eval()
+    o.load_state_dict(synth_state_dict(o, seed=3))
+    b = B200Prior.from_module(o, device=device)
+    b.use_cuda_graph = graph
+    return o, b
+
+
+def test_state_dict_keys_match_reference_layout():
+    o = OraclePrior(n_layer=2)
+    b = B200Prior(n_layer=2, device="meta")
+    assert {k: tuple(v.shape) for k, v in b.state_dict().items()} == {k: tuple(v.shape) for k, v in o.state_dict().items()}
+    assert "model.h.0.attn.c_attn.weight" in b.state_dict() and b.state_dict()["model.h.0.attn.c_attn.weight"].shape == (1024, 3072)
+
+
+@pytest.mark.parametrize("case", G.PRIOR_CASES[:2], ids=[c[0] for c in G.PRIOR_CASES[:2]])
+def test_generate_diffusion_matches_reference_golden(emu, case):
+    name, n_layer, kw = case
+    gold = torch.from_numpy(np.load(GOLD)[name])
+    o, b = build(n_layer)
+    src, clip_hidden = G.prior_inputs(name)
+    b.set_clip_hidden(clip_hidden)
+    torch.manual_seed(1234)
+    y, cond = b.generate_diffusion(3, 0, src, device="cpu", dtype=torch.float32, **kw)
+    assert y.shape == (1, 1, 1024)
+    assert cos(y, gold) > 0.999, cos(y, gold)       # north-star gate: prior output embedding cosine >= 0.999
+
+
+def test_batched_prior_rows_match_per_sample_oracle(emu):
+    """C4 needs 8 samples/GPU; the reference cannot batch (prior/model.py:569,580) -> check rows vs per-sample oracle."""
+    o, b = build(2)
+    clip_hidden = G.prior_inputs("l2_nodiff")[1]
+    b.set_clip_hidden(clip_hidden)
+    srcs = torch.stack([G.prior_inputs(f"b{i}")[0][0] for i in range(3)])
+    torch.manual_seed(7)
+    yb, _ = b.generate_diffusion(3, 0, srcs, device="cpu", dtype=torch.float32, no_diffusion=True, guidance_scale=10, score=6.5)
+    torch.manual_seed(7)
+    noise = torch.randn(3, 1, 1024)
+    for i in range(3):
+        # reproduce the batched draw order for sample i: feed the oracle the i-th row of the batched noise
+        torch.manual_seed(7)
+        import oracle.prior as OP
+        real_randn = torch.randn
+        try:
+            torch.randn = lambda *a, **k: noise[i:i + 1].clone() if tuple(a) == (1, 1, 1024) else real_randn(*a, **k)
+            yo, _ = o.generate_diffusion(3, 0, srcs[i], clip_hidden, no_diffusion=True, guidance_scale=10, score=6.5)
+        finally:
+            torch.randn = real_randn
+        assert cos(yb[i], yo) > 0.9999
