@@ -4,6 +4,8 @@
 //     and one output write (replaces two SDPA calls + add; attention_processor.py:371-397)
 // Round-1 implementation uses warp-level mma.sync m16n8k16 tiles (legacy tensor path, HMMA); the tcgen05/TMEM
 // version is the planned replacement for the self-attention kernel ("next").
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ia2p {
@@ -321,7 +323,21 @@ static int launch_cross(const void* q, int64_t ldq, const void* kt, const void* 
 
 }  // namespace ia2p
 
+namespace ia2p {
+int launch_fa_tc(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int64_t batch,
+                 int64_t n_tokens, int heads, float softmax_scale, cudaStream_t st);
+}
 using namespace ia2p;
+
+// IA2P_ATTN_IMPL=mma selects the round-1 warp-level mma.sync kernel (kept for A/B measurements); default is tcgen05.
+static bool use_legacy_attn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA2P_ATTN_IMPL");
+    v = (e != nullptr && e[0] == 'm') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 extern "C" int ia2p_flash_self_attn_bf16(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo,
                                          int64_t batch, int64_t n_tokens, int heads, float softmax_scale, void* stream) {
@@ -329,6 +345,8 @@ extern "C" int ia2p_flash_self_attn_bf16(const void* q, const void* k, const voi
   IA2P_REQUIRE(q && k && v && out && batch > 0 && n_tokens > 0 && heads > 0, IA2P_E_ARG, "flash_self_attn: bad arguments");
   IA2P_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, IA2P_E_ALIGN, "flash_self_attn: ld/ldo must be multiples of 8");
   IA2P_REQUIRE(heads <= 65535 && batch <= 65535, IA2P_E_SHAPE, "flash_self_attn: heads/batch too large");
+  if (!use_legacy_attn())
+    return launch_fa_tc(q, k, v, ld, out, ldo, batch, n_tokens, heads, softmax_scale, static_cast<cudaStream_t>(stream));
   constexpr int smem = 128 * 128 + 4 * 64 * 128;
   static bool done = false;
   if (!done) {

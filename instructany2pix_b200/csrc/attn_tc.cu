@@ -1,0 +1,290 @@
+// tcgen05 / TMEM / TMA flash self-attention for sm_100a, head_dim 64, non-causal (SDPA at attention_processor.py:259-261).
+//
+// CTA = 128 query rows of one (batch, head); 6 warps: w0 TMA producer, w1 tcgen05.mma issuer (owns TMEM), w2..w5 softmax
+// (one query row per thread, so row max / row sum need no shuffles).  Per 128-key block j:
+//   MMA1: S(TMEM, 128 cols fp32) = Q(smem) K_j^T(smem)                      [M128 N128 K64]
+//   softmax warps: S -> registers (2 passes over TMEM), p = exp2(s*scale - m_ref) -> bf16 -> smem (K-major SW128 A operand)
+//   MMA2: O(TMEM, 64 cols fp32) += P(smem) V_j(smem, MN-major)               [M128 N64 K128]
+// O accumulates in TMEM across blocks; the running reference max m_ref is only raised (and O, l rescaled through
+// tcgen05.ld/st) when a row's block max exceeds it by more than 8 (log2 units), so the rescale path is rare and the
+// result is exact up to the common factor that cancels in O / l.  MMA1 of block j+1 is issued before MMA2 of block j, and
+// two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each), so tensor work overlaps the softmax math.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ia2p {
+
+struct alignas(64) FaMaps {
+  CUtensorMap q, k, v;   // 3-D {heads*64, n_tokens, batch}, box {64, 128, 1}, SWIZZLE_128B
+};
+
+constexpr int kFaTile = 128 * 128;                 // bytes: 128 rows x 64 bf16
+constexpr int kFaSmemTiles = kFaTile * (1 + 2 + 2 + 2);   // Q, K x2, V x2, P (two 64-key halves)
+constexpr int kFaSmemBytes = kFaSmemTiles + 1024;  // barriers live in the alignment slack in front of the tiles
+constexpr float kRescaleThreshold = 8.0f;
+
+__global__ void __launch_bounds__(192, 2)
+fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ out, long long ldo, int n_tokens, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = (raw + 128u + 1023u) & ~1023u;       // >= 128 B of barriers in front
+  if (tiles + kFaSmemTiles > raw + kFaSmemBytes) __trap();    // dynamic smem base less aligned than assumed
+  const uint32_t sQ = tiles, sK = sQ + kFaTile, sV = sK + 2 * kFaTile, sP = sV + 2 * kFaTile;
+  const uint32_t bars = raw;
+  const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, k_empty = bars + 40, v_empty = bars + 56;
+  const uint32_t s_full = bars + 72, s_empty = bars + 80, p_full = bars + 88, pv_full = bars + 96, tmem_slot = bars + 104;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_blocks = (n_tokens + 127) >> 7;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full + 8 * s, 1); mbar_init(v_full + 8 * s, 1);
+      mbar_init(k_empty + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
+    }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kFaTile);
+      tma_load_3d(sQ, &maps.q, q_full, h * 64, q0, b);
+    }
+    for (int j = 0; j < n_blocks; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      mbar_wait(k_empty + 8 * st, ph ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(k_full + 8 * st, kFaTile);
+        tma_load_3d(sK + st * kFaTile, &maps.k, k_full + 8 * st, h * 64, j * 128, b);
+      }
+      mbar_wait(v_empty + 8 * st, ph ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(v_full + 8 * st, kFaTile);
+        tma_load_3d(sV + st * kFaTile, &maps.v, v_full + 8 * st, h * 64, j * 128, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);
+    auto issue_qk = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(k_full + 8 * st, (uint32_t)((j >> 1) & 1));
+      if (j > 0) mbar_wait(s_empty, (uint32_t)((j - 1) & 1));     // softmax finished reading S_{j-1}
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t da = umma_desc_sw128(sQ), db = umma_desc_sw128(sK + st * kFaTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tS, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, (uint32_t)(k != 0));
+        umma_commit(k_empty + 8 * st);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < n_blocks; ++j) {
+      if (j + 1 < n_blocks) issue_qk(j + 1);                      // overlaps the softmax of block j
+      const int st = j & 1;
+      mbar_wait(v_full + 8 * st, (uint32_t)((j >> 1) & 1));
+      mbar_wait(p_full, (uint32_t)(j & 1));                       // P_j in smem; O (TMEM) rescaled if needed
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {                          // 8 x 16 keys
+          const uint64_t da = umma_desc_sw128(sP + (ks >> 2) * kFaTile) + (uint64_t)(2 * (ks & 3));
+          const uint64_t db = umma_desc_sw128_mn(sV + st * kFaTile + ks * 2048, kFaTile);
+          umma_bf16(tO, da, db, idesc_pv, (uint32_t)((j | ks) != 0));
+        }
+        umma_commit(v_empty + 8 * st);
+        umma_commit(pv_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ softmax / epilogue: one query row per thread
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_blocks; ++j) {
+      mbar_wait(s_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      const int kv_left = n_tokens - j * 128;                     // valid keys in this block (>= 1)
+      // pass A: block row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (kv_left >= 128) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      mx *= scale_log2;
+      float alpha = 1.f;
+      bool rescale = false;
+      if (mx > m_ref + kRescaleThreshold) {                       // first block (m_ref = -inf) or a big jump
+        const float m_new = mx;
+        alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+        rescale = (j > 0);
+        m_ref = m_new;
+        l *= alpha;
+      }
+      // pass B: p = exp2(s*scale - m_ref), packed to bf16 (kept in registers until the P buffer is free)
+      uint32_t pk[64];
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = exp2f(__uint_as_float(v[i]) * scale_log2 - m_ref);
+          float p1 = exp2f(__uint_as_float(v[i + 1]) * scale_log2 - m_ref);
+          if (kv_left < 128) {
+            if (c * 32 + i >= kv_left) p0 = 0.f;
+            if (c * 32 + i + 1 >= kv_left) p1 = 0.f;
+          }
+          lsum += p0 + p1;
+          pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+        }
+      }
+      l += lsum;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);                        // S may be overwritten by MMA1 of block j+1
+      // P buffer / O accumulator are free once MMA2 of block j-1 has completed
+      if (j > 0) {
+        mbar_wait(pv_full, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, rescale)) {                   // rare: raise the reference max -> rescale O row-wise
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + lane_sel + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(tO + lane_sel + (uint32_t)(c * 32), v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // write P (K-major, SWIZZLE_128B, two 64-key halves): row r, 16-byte chunk c -> r*128 + ((c ^ (r&7)) << 4)
+      uint8_t* pbase = smem_raw + (sP - raw);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int half = c >> 3, cc = c & 7;
+        *reinterpret_cast<uint4*>(pbase + half * kFaTile + row * 128 + ((cc ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+      fence_proxy_async();                                        // generic-proxy smem writes -> visible to the MMA (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> bf16 -> global (one 128-byte row per thread)
+    mbar_wait(pv_full, (uint32_t)((n_blocks - 1) & 1));
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const bool ok = q0 + row < n_tokens;
+    __nv_bfloat16* op = out + ((long long)b * n_tokens + q0 + row) * ldo + h * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tO + lane_sel + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn fa_get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+static int fa_make_map(CUtensorMap* m, const void* base, int64_t cols, int64_t ld, int64_t n_tokens, int64_t batch) {
+  EncodeTiledFn enc = fa_get_encode();
+  IA2P_REQUIRE(enc != nullptr, IA2P_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IA2P_E_ALIGN, "flash_self_attn: q/k/v base not 16-byte aligned");
+  const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)n_tokens, (cuuint64_t)batch};
+  const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)n_tokens};
+  const cuuint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IA2P_REQUIRE(r == CUDA_SUCCESS, IA2P_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+int launch_fa_tc(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int64_t batch,
+                 int64_t n_tokens, int heads, float softmax_scale, cudaStream_t st) {
+  FaMaps maps;
+  if (int e = fa_make_map(&maps.q, q, heads * 64, ld, n_tokens, batch)) return e;
+  if (int e = fa_make_map(&maps.k, k, heads * 64, ld, n_tokens, batch)) return e;
+  if (int e = fa_make_map(&maps.v, v, heads * 64, ld, n_tokens, batch)) return e;
+  static bool done = false;
+  if (!done) {
+    IA2P_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
+    IA2P_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    done = true;
+  }
+  const dim3 grid((unsigned)((n_tokens + 127) / 128), (unsigned)heads, (unsigned)batch);
+  fa_tc_kernel<<<grid, 192, kFaSmemBytes, st>>>(maps, static_cast<__nv_bfloat16*>(out), ldo, (int)n_tokens,
+                                                softmax_scale * 1.4426950408889634f);
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ia2p

@@ -104,39 +104,54 @@ __global__ void cast_bf16_kernel(const T* __restrict__ x, uint4* __restrict__ y,
     y[i] = load8_as_bf16(x + i * 8);
 }
 
-// ---------------------------------------------------------------- conv_in: NCHW (Cin <= 8) -> NHWC bf16
-// one thread = one output pixel x 8 output channels; weights [Cout,Cin,3,3] fp32 read through L1/constant cache.
+// ---------------------------------------------------------------- conv_in: NCHW (few channels) -> NHWC (bf16|fp32)
+// fp32 CUDA-core conv (K = 9*Cin = 36 is too shallow for tensor cores and the input latents stay unrounded).
+// Block = 64 output pixels: weights transposed to smem [K][Cout], the 64 input patches to smem [64][K]; each thread
+// produces channel quads (float4 weight reads conflict-free, patch reads broadcast), stores are fully coalesced.
+constexpr int kConvInTile = 64;
 template <typename TX, typename TO>
-__global__ void conv_in_kernel(const TX* __restrict__ x, long long in_batch, long long B, int H, int W, int Cin,
-                               const float* __restrict__ w, const float* __restrict__ bias,
-                               TO* __restrict__ out, int Cout) {
-  const int cgroups = Cout / 8;
-  const long long total = B * (long long)H * W * cgroups;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(idx % cgroups);
-    long long pix = idx / cgroups;
-    const int xx = (int)(pix % W);
-    const int yy = (int)((pix / W) % H);
-    const long long b = pix / ((long long)W * H);
-    const long long bi = b % in_batch;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[cg * 8 + j] : 0.f;
-    for (int ci = 0; ci < Cin; ++ci)
-      for (int ky = 0; ky < 3; ++ky) {
-        const int iy = yy + ky - 1;
-        if (iy < 0 || iy >= H) continue;
-        for (int kx = 0; kx < 3; ++kx) {
-          const int ix = xx + kx - 1;
-          if (ix < 0 || ix >= W) continue;
-          const float v = load_as_float(x + ((bi * Cin + ci) * H + iy) * (long long)W + ix);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += v * __ldg(w + (((cg * 8 + j) * Cin + ci) * 3 + ky) * 3 + kx);
-        }
-      }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) store_from_float(out + pix * Cout + cg * 8 + j, acc[j]);
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const TX* __restrict__ x, long long in_batch, long long B, int H, int W, int Cin,
+               const float* __restrict__ w, const float* __restrict__ bias, TO* __restrict__ out, int Cout) {
+  extern __shared__ float sm[];
+  const int K = Cin * 9;
+  float* sw = sm;                       // [K][Cout]
+  float* sp = sm + (size_t)K * Cout;    // [tile][K]
+  const long long npix = B * (long long)H * W;
+  const long long pix0 = (long long)blockIdx.x * kConvInTile;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int co = i / K, k = i - co * K;              // w is [Cout][Cin][3][3] = [Cout][K]
+    sw[k * Cout + co] = w[i];
+  }
+  for (int i = threadIdx.x; i < kConvInTile * K; i += blockDim.x) {
+    const int p = i / K, k = i - p * K;
+    const int ci = k / 9, tap = k - ci * 9;
+    const long long pix = pix0 + p;
+    float v = 0.f;
+    if (pix < npix) {
+      const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
+      const long long b = pix / ((long long)W * H);
+      const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v = load_as_float(x + (((b % in_batch) * Cin + ci) * H + iy) * (long long)W + ix);
+    }
+    sp[i] = v;
+  }
+  __syncthreads();
+  const int cq_n = Cout / 4;
+  for (int idx = threadIdx.x; idx < kConvInTile * cq_n; idx += blockDim.x) {
+    const int p = idx / cq_n, cq = idx - p * cq_n;
+    const long long pix = pix0 + p;
+    if (pix >= npix) continue;
+    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* pp = sp + p * K;
+    for (int k = 0; k < K; ++k) {
+      const float v = pp[k];
+      const float4 wv = *reinterpret_cast<const float4*>(sw + k * Cout + cq * 4);
+      acc.x += v * wv.x; acc.y += v * wv.y; acc.z += v * wv.z; acc.w += v * wv.w;
+    }
+    TO* o = out + pix * Cout + cq * 4;
+    store_from_float(o, acc.x); store_from_float(o + 1, acc.y); store_from_float(o + 2, acc.z); store_from_float(o + 3, acc.w);
   }
 }
 
@@ -289,18 +304,25 @@ extern "C" int ia2p_conv_in_nchw(const void* x, int x_dtype, int64_t in_batch, i
   if (int e = check_device()) return e;
   IA2P_REQUIRE(x && w && out && B > 0 && in_batch > 0 && H > 0 && W > 0, IA2P_E_ARG, "conv_in: bad arguments");
   IA2P_REQUIRE(out_dtype == IA2P_BF16 || out_dtype == IA2P_F32, IA2P_E_ARG, "conv_in: out_dtype must be bf16 or f32");
-  IA2P_REQUIRE(Cin >= 1 && Cin <= 16 && Cout % 8 == 0, IA2P_E_SHAPE, "conv_in: Cin<=16 and Cout%%8==0 required");
+  IA2P_REQUIRE(Cin >= 1 && Cin <= 8 && Cout % 8 == 0 && Cout <= 640, IA2P_E_SHAPE, "conv_in: Cin<=8, Cout%%8==0, Cout<=640 required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = grid_for(B * H * W * (Cout / 8), 256);
+  const long long npix = B * H * W;
+  const unsigned grid = (unsigned)((npix + kConvInTile - 1) / kConvInTile);
+  const size_t smem = (size_t)Cin * 9 * (Cout + kConvInTile) * sizeof(float);
+  IA2P_REQUIRE(smem <= 200 * 1024, IA2P_E_SHAPE, "conv_in: shared-memory footprint too large");
+#define IA2P_CONV_IN(TX_, TO_)                                                                                           \
+  do {                                                                                                                   \
+    if (smem > 48 * 1024)                                                                                                \
+      IA2P_CUDA(cudaFuncSetAttribute(conv_in_kernel<TX_, TO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_in_kernel<TX_, TO_><<<grid, 256, smem, st>>>(static_cast<const TX_*>(x), in_batch, B, (int)H, (int)W, (int)Cin, w, \
+                                                      bias, static_cast<TO_*>(out), (int)Cout);                         \
+  } while (0)
   if (out_dtype == IA2P_BF16) {
-    DISPATCH_DTYPE(x_dtype, TX,
-        (conv_in_kernel<TX, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const TX*>(x), in_batch, B, (int)H, (int)W, (int)Cin,
-                                                                 w, bias, static_cast<__nv_bfloat16*>(out), (int)Cout)));
+    DISPATCH_DTYPE(x_dtype, TX, IA2P_CONV_IN(TX, __nv_bfloat16));
   } else {
-    DISPATCH_DTYPE(x_dtype, TX,
-        (conv_in_kernel<TX, float><<<grid, 256, 0, st>>>(static_cast<const TX*>(x), in_batch, B, (int)H, (int)W, (int)Cin, w,
-                                                         bias, static_cast<float*>(out), (int)Cout)));
+    DISPATCH_DTYPE(x_dtype, TX, IA2P_CONV_IN(TX, float));
   }
+#undef IA2P_CONV_IN
   IA2P_LAUNCH_CHECK();
   return 0;
 }
