@@ -51,11 +51,11 @@ struct TcCfg {
   static constexpr int A_BYTES = 128 * 128;             // 128 rows x 64 bf16
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 160 ? 5 : 6);
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGE_OFF = STAGES * STAGE_BYTES + BAR_BYTES;            // epilogue staging, from smem_base
-  static constexpr int EPI_BYTES = 4 * 32 * kStageLd * 4 + 128 * 8 + 128 * 4;   // 4 warp tiles + pixel index + batch index
+  static constexpr int EPI_BYTES = 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_BYTES;
 };
 
@@ -158,20 +158,18 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (4 warps)
-    // TMEM -> registers gives one accumulator ROW per thread; global traffic wants one row SEGMENT per 8 lanes.  Each
-    // 32-column chunk is therefore transposed through a per-warp smem staging tile: phase 1 writes row-per-lane,
-    // phase 2 reads 4 rows x 32 columns per instruction (8 lanes x float4 per row) so that every residual load and
-    // every output store covers whole 128-byte (fp32) / 64-byte (bf16) row segments.
+    // ------------------------------------------------------------ epilogue (4 warps, one accumulator row per thread)
+    // TMEM -> registers hands every thread one output row.  Shared memory is NOT used here on purpose: with
+    // cta_group::1 the UMMA operand reads already run close to the smem bandwidth, and staging the tile through smem for
+    // a transposed (fully coalesced) store measurably starves the MMA.  Instead each thread moves whole 32-byte sectors
+    // with 256-bit global accesses, and the fp32 residual (independent of the accumulator) is fetched two 32-column
+    // chunks ahead -- the first two before waiting for the MMA -- so its latency hides behind the main loop.
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int tw = row & ((1 << p.tw_log2) - 1);
     const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
     const int tb = row >> (p.tw_log2 + p.th_log2);
-    float* stage = reinterpret_cast<float*>(smem_raw + (Cfg::STAGE_OFF + smem_base - smem_u32(smem_raw))) + q * (32 * kStageLd);
-    long long* spix = reinterpret_cast<long long*>(smem_raw + (Cfg::STAGE_OFF + 4 * 32 * kStageLd * 4 + smem_base - smem_u32(smem_raw)));
-    int* sbat = reinterpret_cast<int*>(spix + 128);
-    const int rsub = lane >> 3, cq = lane & 7;
+    constexpr int NCH = BLOCK_N / 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -184,76 +182,122 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
       const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
       const int n0 = n_tile * BLOCK_N;
-      __syncwarp();
-      spix[row] = valid ? pix : -1;
-      sbat[row] = (valid && p.rowbias != nullptr) ? (int)(pix / p.rows_per_batch) : 0;
-      __syncwarp();
+      const float* rb = (p.rowbias != nullptr && valid) ? p.rowbias + (pix / p.rows_per_batch) * (long long)p.N : nullptr;
+      const bool res32 = (p.residual != nullptr) && p.res_f32 && valid && !p.geglu;
+      const float* res_row = static_cast<const float*>(p.residual) + pix * p.ldr;
+
+      float rpre[2][32];
+      auto load_res = [&](int c, float (&dst)[32]) {
+        if (n0 + c * 32 < p.N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ldg256(res_row + n0 + c * 32 + i * 8, &dst[i * 8]);
+        }
+      };
+      if (res32) {
+        load_res(0, rpre[0]);
+        if (NCH > 1) load_res(1, rpre[1]);
+      }
 
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N);
-      const int n_chunks = p.geglu ? BLOCK_N / 64 : BLOCK_N / 32;
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        const int n = n0 + c * (p.geglu ? 64 : 32);           // GEMM column of this chunk
-        if (n >= p.N) break;                                   // warp-uniform
-        uint32_t v[32];
-        if (!p.geglu) {
-          tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
-          tmem_ld_wait();
-        } else {
-          // GEGLU: W rows interleaved in 32-row groups [value | gate]; out col = n/2 + i:  value * gelu_erf(gate)
-          uint32_t vg[32];
-          tmem_ld_32x32(t_row + (uint32_t)(c * 64), v);
-          tmem_ld_32x32(t_row + (uint32_t)(c * 64 + 32), vg);
-          tmem_ld_wait();
+
+      if (!p.geglu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = __uint_as_float(v[i]), g = __uint_as_float(vg[i]);
-            if (p.bias != nullptr) { a += __ldg(p.bias + n + i); g += __ldg(p.bias + n + 32 + i); }
-            v[i] = __float_as_uint(a * gelu_erf_f(g));
-          }
-        }
-        // phase 1: row-per-lane -> staging (row stride 36 floats: conflict-free 16-byte stores)
+        for (int c = 0; c < NCH; ++c) {
+          const int n = n0 + c * 32;
+          if (n < p.N) {                                         // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+            if (valid) {
+              float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(stage + lane * kStageLd + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        __syncwarp();
-        // phase 2: 8 lanes per row segment
-        const int ncol = p.geglu ? (n >> 1) + cq * 4 : n + cq * 4;   // output column of this lane's 4 values
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!p.geglu && p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+              if (p.bias != nullptr) {
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rr = itr * 4 + rsub;
-          const long long px = spix[q * 32 + rr];
-          if (px < 0) continue;
-          float4 a = *reinterpret_cast<const float4*>(stage + rr * kStageLd + cq * 4);
-          a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-          if (p.rowbias != nullptr) {
-            const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)sbat[q * 32 + rr] * p.N + ncol));
-            a.x += rb.x; a.y += rb.y; a.z += rb.z; a.w += rb.w;
-          }
-          if (p.residual != nullptr) {
-            if (p.res_f32) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + px * p.ldr + ncol));
-              a.x += rv.x; a.y += rv.y; a.z += rv.z; a.w += rv.w;
-            } else {
-              const uint2 rv = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.residual) + px * p.ldr + ncol));
-              const float2 t0 = unpack_bf16x2(rv.x), t1 = unpack_bf16x2(rv.y);
-              a.x += t0.x; a.y += t0.y; a.z += t1.x; a.w += t1.y;
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                  f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+                }
+              }
+              if (rb != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+                  f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+                }
+              }
+              if (res32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] += rpre[c & 1][i];
+                if (c + 2 < NCH) load_res(c + 2, rpre[c & 1]);
+              } else if (p.residual != nullptr) {
+                if (p.res_f32) {   // (unreachable: res32 covers it) kept for clarity
+                } else {
+                  const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + n);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const uint4 rv = __ldg(rp + i);
+                    float2 t;
+                    t = unpack_bf16x2(rv.x); f[8 * i + 0] += t.x; f[8 * i + 1] += t.y;
+                    t = unpack_bf16x2(rv.y); f[8 * i + 2] += t.x; f[8 * i + 3] += t.y;
+                    t = unpack_bf16x2(rv.z); f[8 * i + 4] += t.x; f[8 * i + 5] += t.y;
+                    t = unpack_bf16x2(rv.w); f[8 * i + 6] += t.x; f[8 * i + 7] += t.y;
+                  }
+                }
+              }
+              if (p.out_f32) {
+                float* op = static_cast<float*>(p.out) + pix * p.ldo + n;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) stg256(op + i * 8, &f[i * 8]);
+              } else {
+                __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + n;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  float o[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(pack_bf16x2(f[16 * i + 2 * k], f[16 * i + 2 * k + 1]));
+                  stg256(reinterpret_cast<float*>(op + i * 16), o);
+                }
+              }
             }
           }
-          if (p.out_f32) {
-            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + px * p.ldo + ncol) = a;
-          } else {
-            uint2 o;
-            o.x = pack_bf16x2(a.x, a.y);
-            o.y = pack_bf16x2(a.z, a.w);
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + px * p.ldo + ncol) = o;
+        }
+      } else {
+        // GEGLU: W rows interleaved in 32-row groups [value | gate]; out col = n/2 + i:  value * gelu_erf(gate)
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          const int n = n0 + c * 64;
+          if (n >= p.N) break;                                   // warp-uniform
+          uint32_t vv[32], vg[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 64), vv);
+          tmem_ld_32x32(t_row + (uint32_t)(c * 64 + 32), vg);
+          tmem_ld_wait();
+          if (valid) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+              if (p.bias != nullptr) {
+                bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32 + i));
+              }
+              f[i + 0] = (__uint_as_float(vv[i + 0]) + bv.x) * gelu_erf_f(__uint_as_float(vg[i + 0]) + bg.x);
+              f[i + 1] = (__uint_as_float(vv[i + 1]) + bv.y) * gelu_erf_f(__uint_as_float(vg[i + 1]) + bg.y);
+              f[i + 2] = (__uint_as_float(vv[i + 2]) + bv.z) * gelu_erf_f(__uint_as_float(vg[i + 2]) + bg.z);
+              f[i + 3] = (__uint_as_float(vv[i + 3]) + bv.w) * gelu_erf_f(__uint_as_float(vg[i + 3]) + bg.w);
+            }
+            __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + (n >> 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(pack_bf16x2(f[16 * i + 2 * k], f[16 * i + 2 * k + 1]));
+              stg256(reinterpret_cast<float*>(op + i * 16), o);
+            }
           }
         }
-        __syncwarp();      // staging tile is reused by the next chunk
       }
       tc_fence_before();
       __syncwarp();
@@ -374,6 +418,11 @@ extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void
   IA2P_REQUIRE(lda % 8 == 0 && ldo % 8 == 0 && (A2 == nullptr || lda2 % 8 == 0) && (residual == nullptr || ldr % 8 == 0),
                IA2P_E_ALIGN, "gemm: leading dimensions must be multiples of 8 elements");
   IA2P_REQUIRE((A2 == nullptr) == (K2 == 0), IA2P_E_ARG, "gemm: A2 and K2 must be given together");
+  // the epilogue moves 32-byte sectors (256-bit global accesses)
+  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(out) & 31) == 0 && (ldo * (out_dtype == IA2P_F32 ? 4 : 2)) % 32 == 0, IA2P_E_ALIGN,
+               "gemm: out must be 32-byte aligned with a 32-byte-multiple row pitch (ldo=%lld)", (long long)ldo);
+  IA2P_REQUIRE(residual == nullptr || res_dtype != IA2P_F32 || ((reinterpret_cast<uintptr_t>(residual) & 31) == 0 && ldr % 8 == 0),
+               IA2P_E_ALIGN, "gemm: fp32 residual must be 32-byte aligned with ldr%%8==0");
   const bool geglu = epilogue == IA2P_EPI_GEGLU;
   IA2P_REQUIRE(!geglu || (N % 64 == 0 && residual == nullptr && rowbias == nullptr && out_dtype == IA2P_BF16), IA2P_E_ARG, "gemm: GEGLU needs N%%64==0, bf16 output and no residual/rowbias");
   IA2P_REQUIRE(rowbias == nullptr || rows_per_batch > 0, IA2P_E_ARG, "gemm: rowbias needs rows_per_batch");
@@ -429,6 +478,8 @@ extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64
   IA2P_REQUIRE((sc_a == nullptr) == (sc_ca == 0) && (sc_b == nullptr) == (sc_cb == 0) && (sc_b == nullptr || sc_a != nullptr),
                IA2P_E_ARG, "conv3x3: inconsistent shortcut sources");
   IA2P_REQUIRE(stride == 1 || (sc_a == nullptr && H % 2 == 0 && W % 2 == 0), IA2P_E_ARG, "conv3x3: stride 2 needs even H,W and no shortcut");
+  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(out) & 31) == 0 && (residual == nullptr || (reinterpret_cast<uintptr_t>(residual) & 31) == 0),
+               IA2P_E_ALIGN, "conv3x3: out/residual must be 32-byte aligned");
   const int64_t Ho = H / stride, Wo = W / stride;
   // tile: largest power-of-two divisors
   int TW = 1; while (TW < 128 && Wo % (TW * 2) == 0) TW *= 2;
