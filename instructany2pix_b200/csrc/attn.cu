@@ -177,7 +177,7 @@ flash_self_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
 // ================================================================ decoupled cross-attention
 // All keys resident in smem: text keys padded to T1 (multiple of 16), IP keys padded to T2 (0 or 16).
 template <int T1, int T2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (T1 <= 96) ? 3 : 1)
 cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kt,
                   const __nv_bfloat16* __restrict__ vt, long long ldkv, int n_text, const __nv_bfloat16* __restrict__ ki,
                   const __nv_bfloat16* __restrict__ vi, long long ldkv_ip, int n_ip, float ip_scale,

@@ -127,49 +127,63 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       mbar_wait(s_full, (uint32_t)(j & 1));
       tc_fence_after();
       const int kv_left = n_tokens - j * 128;                     // valid keys in this block (>= 1)
-      // pass A: block row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        if (kv_left >= 128) {
+      const bool ragged = kv_left < 128;                          // only the last block can be ragged
+      uint32_t pk[64];
+      float lsum = 0.f, alpha = 1.f;
+      // FAST PATH (every block but the first): one pass, p = 2^(s*scale - m_ref) against the standing reference max.
+      // bf16 / fp32 share the exponent range, so p may exceed 1 by many orders without harm; the reference is only
+      // raised when a row's block sum shows it is stale by > 2^20 (or on the first / ragged block) -> SLOW PATH below.
+      bool slow = (j == 0) || ragged;
+      if (!slow) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
+            lsum += p0 + p1;
+            pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+          }
         }
+        slow = !(lsum < 1048576.f);                               // also catches inf / nan
       }
-      mx *= scale_log2;
-      float alpha = 1.f;
-      bool rescale = false;
-      if (mx > m_ref + kRescaleThreshold) {                       // first block (m_ref = -inf) or a big jump
-        const float m_new = mx;
-        alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
-        rescale = (j > 0);
+      const bool any_slow = __any_sync(0xffffffffu, slow);
+      if (any_slow) {
+        // SLOW PATH (warp-uniform): exact block row max -> raise the reference, recompute p, remember alpha for O and l
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (!ragged || c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        const float m_new = fmaxf(m_ref, mx * scale_log2);
+        alpha = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new);
         m_ref = m_new;
         l *= alpha;
-      }
-      // pass B: p = exp2(s*scale - m_ref), packed to bf16 (kept in registers until the P buffer is free)
-      uint32_t pk[64];
-      float lsum = 0.f;
+        lsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(__uint_as_float(v[i]) * scale_log2 - m_ref);
-          float p1 = exp2f(__uint_as_float(v[i + 1]) * scale_log2 - m_ref);
-          if (kv_left < 128) {
-            if (c * 32 + i >= kv_left) p0 = 0.f;
-            if (c * 32 + i + 1 >= kv_left) p1 = 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
+            if (ragged) {
+              if (c * 32 + i >= kv_left) p0 = 0.f;
+              if (c * 32 + i + 1 >= kv_left) p1 = 0.f;
+            }
+            lsum += p0 + p1;
+            pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
           }
-          lsum += p0 + p1;
-          pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
         }
       }
       l += lsum;
@@ -180,7 +194,7 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       if (j > 0) {
         mbar_wait(pv_full, (uint32_t)((j - 1) & 1));
         tc_fence_after();
-        if (__any_sync(0xffffffffu, rescale)) {                   // rare: raise the reference max -> rescale O row-wise
+        if (any_slow) {                                           // rare: reference raised -> rescale O row-wise in TMEM
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t v[32];

@@ -12,6 +12,7 @@
 // main loop of tile i+1.  Tile 128 x BLOCK_N x 64, operands K-major SWIZZLE_128B.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -45,13 +46,16 @@ struct TcParams {
   int geglu, out_f32, res_f32;
 };
 
-constexpr int kStageLd = 36;                              // epilogue staging row stride (floats): 144 B, 16-B aligned
-template <int BLOCK_N>
+// CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BLOCK_N tile:
+// each CTA stages its own 128 A rows and HALF of the B rows, so the per-SM shared-memory traffic per MMA cycle drops by a
+// third -- with CG = 1 the UMMA operand reads + TMA writes (192 B/clk at 128x256x64) exceed what smem sustains and cap the
+// main loop near 55 % of the tensor peak (measured, profiles/README.md).
+template <int BLOCK_N, int CG = 1>
 struct TcCfg {
   static constexpr int A_BYTES = 128 * 128;             // 128 rows x 64 bf16
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_BYTES = (BLOCK_N / CG) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int STAGES = (STAGE_BYTES > 40 * 1024) ? 4 : (STAGE_BYTES > 36 * 1024 ? 5 : 6);
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGE_OFF = STAGES * STAGE_BYTES + BAR_BYTES;            // epilogue staging, from smem_base
@@ -59,10 +63,14 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_BYTES;
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+constexpr int kEpiWarps = 8;                            // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+
+template <int BLOCK_N, int CG>
+__global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, CG>;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs), 1 = peer
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -81,37 +89,42 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     tma_prefetch_desc(&maps.w);
     tma_prefetch_desc(&maps.a[0]);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 1);               // CG = 2: the leader expects BOTH CTAs' TMA bytes on its barrier
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);
+      mbar_init(tempty_bar(b), kEpiWarps * CG);   // CG = 2: both CTAs' epilogue warps release the leader's MMA warp
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();        // peer barriers must be initialised before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // tile walk: CG = 2 steps over tile PAIRS (two consecutive m-tiles); this CTA owns m_tile = 2 * pair + rank
+  const int m_units = (p.m_tiles + CG - 1) / CG;
+  const int total_tiles = m_units * p.n_tiles;
+  const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
   const int TB = 128 >> (p.tw_log2 + p.th_log2);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+    for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+      const int m_unit = tile / p.n_tiles, n_tile = tile - m_unit * p.n_tiles;
+      const int m_tile = m_unit * CG + (int)rank;       // may be == m_tiles for the odd tail: TMA zero-fills (batch coord OOB)
       const int xt = m_tile % p.tiles_x;
       const int r = m_tile / p.tiles_x;
       const int yt = r % p.tiles_y, bt = r / p.tiles_y;
-      const int x0 = xt << p.tw_log2, y0 = yt << p.th_log2, b0 = bt * TB, n0 = n_tile * BLOCK_N;
+      const int x0 = xt << p.tw_log2, y0 = yt << p.th_log2, b0 = bt * TB;
+      const int n0 = n_tile * BLOCK_N + (int)rank * (BLOCK_N / CG);   // this CTA's slice of the B rows
       for (int e = 0; e < p.ntaps; ++e) {
         const TapEntry t = p.taps[e];
         const CUtensorMap* am = &maps.a[t.map_id];
@@ -119,9 +132,19 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (lane == 0) {
             const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-            tma_load_4d(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
-            tma_load_2d(a_dst + Cfg::A_BYTES, &maps.w, full_bar(stage), t.wk0 + c * 64, n0);
+            if (CG == 2) {
+              // Both CTAs' loads complete on the LEADER's full barrier (peer-bit-masked address).  Only the leader arrives
+              // (expecting the bytes of both CTAs): a remote arrive per k-block from the peer costs ~1 us of release latency
+              // and starves the MMA (measured).  The signed tx-count makes early peer completions harmless, and the peer
+              // cannot run a phase ahead because its stage is only freed by the leader's multicast commit.
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_2sm(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
+              tma_load_2d_2sm(a_dst + Cfg::A_BYTES, &maps.w, full_bar(stage), t.wk0 + c * 64, n0);
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+              tma_load_4d(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
+              tma_load_2d(a_dst + Cfg::A_BYTES, &maps.w, full_bar(stage), t.wk0 + c * 64, n0);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -129,12 +152,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
+    // ------------------------------------------------------------ MMA issuer (CG = 2: leader CTA only)
+    constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < total_tiles && rank == 0; tile += unit_step, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
@@ -148,10 +171,17 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) per 64-wide K block: +32 B inside the swizzle atom
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          umma_commit(empty_bar(stage));
-          if (kb == p.num_kb - 1) umma_commit(tfull_bar(buf));
+          for (int k = 0; k < 4; ++k) {   // 4 x UMMA_K(16) per 64-wide K block: +32 B inside the swizzle atom
+            if (CG == 2) umma_bf16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          if (CG == 2) {
+            umma_commit_2sm_mc(empty_bar(stage), 3);             // frees this stage in BOTH CTAs
+            if (kb == p.num_kb - 1) umma_commit_2sm_mc(tfull_bar(buf), 3);
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kb == p.num_kb - 1) umma_commit(tfull_bar(buf));
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -164,22 +194,27 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // a transposed (fully coalesced) store measurably starves the MMA.  Instead each thread moves whole 32-byte sectors
     // with 256-bit global accesses, and the fp32 residual (independent of the accumulator) is fetched two 32-column
     // chunks ahead -- the first two before waiting for the MMA -- so its latency hides behind the main loop.
-    const int q = warp & 3;
+    const int q = warp & 3;                               // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                     // 0: first half of the tile's 32-column chunks, 1: second half
     const int row = q * 32 + lane;
     const int tw = row & ((1 << p.tw_log2) - 1);
     const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
     const int tb = row >> (p.tw_log2 + p.th_log2);
     constexpr int NCH = BLOCK_N / 32;
+    constexpr int NCH0 = (NCH + 1) / 2;                   // chunks [0, NCH0) -> half 0, [NCH0, NCH) -> half 1
+    const int c_lo = half == 0 ? 0 : NCH0, c_hi = half == 0 ? NCH0 : NCH;
+    const uint32_t tempty_leader0 = (CG == 2 && rank != 0) ? mapa_shared(tempty_bar(0), 0) : 0u;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int m_unit = tile / p.n_tiles, n_tile = tile - m_unit * p.n_tiles;
+      const int m_tile = m_unit * CG + (int)rank;
       const int xt = m_tile % p.tiles_x;
       const int r = m_tile / p.tiles_x;
       const int yt = r % p.tiles_y, bt = r / p.tiles_y;
       const int x = (xt << p.tw_log2) + tw, y = (yt << p.th_log2) + th, b = bt * TB + tb;
-      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B) && (m_tile < p.m_tiles);
       const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
       const int n0 = n_tile * BLOCK_N;
       const float* rb = (p.rowbias != nullptr && valid) ? p.rowbias + (pix / p.rows_per_batch) * (long long)p.N : nullptr;
@@ -194,8 +229,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       };
       if (res32) {
-        load_res(0, rpre[0]);
-        if (NCH > 1) load_res(1, rpre[1]);
+        load_res(c_lo, rpre[0]);
+        if (c_lo + 1 < c_hi) load_res(c_lo + 1, rpre[1]);
       }
 
       mbar_wait(tfull_bar(buf), use & 1u);
@@ -204,9 +239,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
       if (!p.geglu) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int cc = 0; cc < NCH0; ++cc) {
+          const int c = c_lo + cc;
           const int n = n0 + c * 32;
-          if (n < p.N) {                                         // warp-uniform
+          if (c < c_hi && n < p.N) {                             // warp-uniform
             uint32_t v[32];
             tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
             tmem_ld_wait();
@@ -230,8 +266,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               }
               if (res32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] += rpre[c & 1][i];
-                if (c + 2 < NCH) load_res(c + 2, rpre[c & 1]);
+                for (int i = 0; i < 32; ++i) f[i] += rpre[cc & 1][i];
+                if (c + 2 < c_hi) load_res(c + 2, rpre[cc & 1]);
               } else if (p.residual != nullptr) {
                 if (p.res_f32) {   // (unreachable: res32 covers it) kept for clarity
                 } else {
@@ -267,7 +303,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       } else {
         // GEGLU: W rows interleaved in 32-row groups [value | gate]; out col = n/2 + i:  value * gelu_erf(gate)
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 64; ++c) {
+        for (int c = half; c < BLOCK_N / 64; c += 2) {           // value/gate chunk pairs alternate between the two halves
           const int n = n0 + c * 64;
           if (n >= p.N) break;                                   // warp-uniform
           uint32_t vv[32], vg[32];
@@ -301,16 +337,19 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (lane == 0) {
+        if (CG == 2 && rank != 0) mbar_arrive_cluster(tempty_leader0 + 8u * buf);   // release the LEADER's MMA warp
+        else mbar_arrive(tempty_bar(buf));
+      }
     }
   }
 
   // ------------------------------------------------------------ teardown
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();        // both CTAs done with TMEM / no remote arrive in flight
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -357,6 +396,10 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 }
 
 static int pick_block_n(int64_t N, bool geglu) {
+  if (const char* e = getenv("IA2P_GEMM_BN")) {          // experiments only
+    const int v = atoi(e);
+    if ((v == 128 || v == 160 || v == 256) && N % v == 0 && (!geglu || v % 64 == 0)) return v;
+  }
   if (geglu) return (N % 256 == 0) ? 256 : 128;
   if (N % 256 == 0) return 256;
   if (N % 160 == 0) return 160;
@@ -364,34 +407,62 @@ static int pick_block_n(int64_t N, bool geglu) {
   return 128;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CG>;
   static bool attr_done = false;   // benign race: idempotent
   if (!attr_done) {
-    IA2P_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    IA2P_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   p.n_tiles = (p.N + BN - 1) / BN;
-  const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
-  tc_gemm_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(maps, p);
+  const int units = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
+  const int max_units = sm_count() / CG;
+  const int grid = (units < max_units ? units : max_units) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IA2P_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG>, maps, p));
   IA2P_LAUNCH_CHECK();
   return 0;
 }
 
+// CTA-pair (cta_group::2) variant: measured on B200 (profiles/README.md) it matches the single-CTA kernel within +-4 % --
+// the single-CTA main loop already keeps the tensor pipe ~81 % active at the power-capped clock -- so the simpler kernel is the
+// default and IA2P_GEMM_CG=2 selects the pair kernel (kept: it halves the L2->smem operand traffic and frees smem for a
+// TMA-staged epilogue).
+static int gemm_cg_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA2P_GEMM_CG");
+    v = (e != nullptr && e[0] == '2') ? 2 : 1;
+  }
+  return v;
+}
+
 static int dispatch_tc(const TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
+  const bool pair = gemm_cg_override() == 2 && p.m_tiles >= 2;
   switch (bn) {
-    case 256: return launch_tc<256>(maps, p, st);
-    case 160: return launch_tc<160>(maps, p, st);
-    default: return launch_tc<128>(maps, p, st);
+    case 256: return pair ? launch_tc<256, 2>(maps, p, st) : launch_tc<256, 1>(maps, p, st);
+    case 160: return pair ? launch_tc<160, 2>(maps, p, st) : launch_tc<160, 1>(maps, p, st);
+    default: return pair ? launch_tc<128, 2>(maps, p, st) : launch_tc<128, 1>(maps, p, st);
   }
 }
 
-static int make_w_map(TcMaps& maps, const void* W, int64_t N, int64_t Ktot, int bn) {
+static int make_w_map(TcMaps& maps, const void* W, int64_t N, int64_t Ktot, int bn, int m_tiles) {
+  const bool pair = gemm_cg_override() == 2 && m_tiles >= 2;      // must mirror dispatch_tc: a CTA of a pair loads BN/2 rows
   const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
   const uint64_t str[2] = {1, (uint64_t)Ktot};
-  const uint32_t box[2] = {64, (uint32_t)bn};
+  const uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
   return make_map(&maps.w, W, 2, dims, str, box);
 }
 
@@ -448,7 +519,7 @@ extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void
     p.taps[1] = TapEntry{1, 0, 0, (int16_t)(K2 / 64), (int32_t)K1};
     p.ntaps = 2;
   }
-  if (int e = make_w_map(maps, W, N, K1 + K2, bn)) return e;
+  if (int e = make_w_map(maps, W, N, K1 + K2, bn, (int)((M + 127) / 128))) return e;
   p.num_kb = (int)((K1 + K2) / 64);
   p.tw_log2 = 7; p.th_log2 = 0;
   p.tiles_x = (int)((M + 127) / 128); p.tiles_y = 1;
@@ -528,7 +599,7 @@ extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64
       }
   }
   p.ntaps = nt;
-  if (int e = make_w_map(maps, w, Cout, Ktot, bn)) return e;
+  if (int e = make_w_map(maps, w, Cout, Ktot, bn, (int)((Wo / TW) * (Ho / TH) * ((B + TB - 1) / TB)))) return e;
   p.num_kb = (int)(Ktot / 64);
   p.tw_log2 = ilog2_exact(TW); p.th_log2 = ilog2_exact(TH);
   p.tiles_x = (int)(Wo / TW); p.tiles_y = (int)(Ho / TH);

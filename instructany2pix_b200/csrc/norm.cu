@@ -23,14 +23,9 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 template <> struct Vec8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
-    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
-    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
-  }
+  // one full 32-byte sector per lane per instruction (LDG.256 / STG.256); rows are 32-byte aligned (cols % 8 == 0)
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) { ldg256(p, f); }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[8]) { stg256(p, f); }
 };
 
 // ---------------------------------------------------------------- GroupNorm statistics
@@ -57,11 +52,27 @@ __global__ void gn_stats_kernel(const T* __restrict__ xa, int ca, const T* __res
   const bool from_a = c0 < ca;
   const T* src = from_a ? xa + b * hw * ca + c0 : xb + b * hw * cb + (c0 - ca);
   const int ld = from_a ? ca : cb;
-  for (long long p = p_begin + threadIdx.y; p < p_end; p += blockDim.y) {
-    float f[8];
-    Vec8<T>::load(src + p * ld, f);
+  {
+    const long long step = blockDim.y;
+    long long p = p_begin + threadIdx.y;
+    for (; p + 3 * step < p_end; p += 4 * step) {          // 4 independent loads in flight per thread
+      float f0[8], f1[8], f2[8], f3[8];
+      Vec8<T>::load(src + p * ld, f0);
+      Vec8<T>::load(src + (p + step) * ld, f1);
+      Vec8<T>::load(src + (p + 2 * step) * ld, f2);
+      Vec8<T>::load(src + (p + 3 * step) * ld, f3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+      for (int j = 0; j < 8; ++j) {
+        s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+        ss[j] += (f0[j] * f0[j] + f1[j] * f1[j]) + (f2[j] * f2[j] + f3[j] * f3[j]);
+      }
+    }
+    for (; p < p_end; p += step) {
+      float f[8];
+      Vec8<T>::load(src + p * ld, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+    }
   }
   float* mine = sm + (size_t)threadIdx.y * 2 * C;
 #pragma unroll
@@ -95,18 +106,30 @@ __global__ void gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __res
   const double cnt = (double)hw * cpg;
   float* gmean = sm + 2 * C;
   float* grstd = gmean + groups;
-  for (int g = tid; g < groups; g += nthr) {
-    double a = 0.0, q = 0.0;
-    for (int sl = 0; sl < (int)gridDim.x; ++sl) {        // fixed slab order: bit-reproducible
-      const double* src = partials + ((b * gridDim.x + sl) * groups + g) * 2;
-      a += src[0];
-      q += src[1];
+  // per-group totals from the per-slab partials: warp w takes groups w, w+nwarps, ...; lanes stride over the slabs and a
+  // fixed-order shuffle tree folds them (bit-reproducible, and every load of the reduction is in flight at once)
+  {
+    const int lane = tid & 31, wid = tid >> 5, nwarps = (nthr + 31) >> 5;
+    for (int g = wid; g < groups; g += nwarps) {
+      double a = 0.0, q = 0.0;
+      for (int sl = lane; sl < (int)gridDim.x; sl += 32) {
+        const double2 v = *reinterpret_cast<const double2*>(partials + ((b * gridDim.x + sl) * groups + g) * 2);
+        a += v.x;
+        q += v.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) {
+        const double mean = a / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gmean[g] = (float)mean;
+        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+      }
     }
-    const double mean = a / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    gmean[g] = (float)mean;
-    grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
   for (int c = tid; c < C; c += nthr) {
@@ -126,9 +149,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __res
   const long long p_begin = (long long)blockIdx.x * pix_per_slab;
   long long p_end = p_begin + pix_per_slab;
   if (p_end > hw) p_end = hw;
-  for (long long p = p_begin + threadIdx.y; p < p_end; p += blockDim.y) {
-    float f[8];
-    Vec8<T>::load(src + p * ld, f);
+  auto emit = [&](long long p, float (&f)[8]) {
     if (raw != nullptr) Vec8<__nv_bfloat16>::store(raw + (b * hw + p) * C + c0, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -136,6 +157,23 @@ __global__ void gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __res
       if (silu) f[j] = silu_f(f[j]);
     }
     Vec8<__nv_bfloat16>::store(y + (b * hw + p) * C + c0, f);
+  };
+  {
+    const long long step = blockDim.y;
+    long long p = p_begin + threadIdx.y;
+    for (; p + 3 * step < p_end; p += 4 * step) {
+      float f0[8], f1[8], f2[8], f3[8];
+      Vec8<T>::load(src + p * ld, f0);
+      Vec8<T>::load(src + (p + step) * ld, f1);
+      Vec8<T>::load(src + (p + 2 * step) * ld, f2);
+      Vec8<T>::load(src + (p + 3 * step) * ld, f3);
+      emit(p, f0); emit(p + step, f1); emit(p + 2 * step, f2); emit(p + 3 * step, f3);
+    }
+    for (; p < p_end; p += step) {
+      float f[8];
+      Vec8<T>::load(src + p * ld, f);
+      emit(p, f);
+    }
   }
 }
 
