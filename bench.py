@@ -162,12 +162,21 @@ def profile_dominant_kernel(unet, sampler, dev_in, B):
     unet.forward_core(x, rb, kv, 2 * B)
     torch.cuda.synchronize()
     rec, ops.PROFILE = ops.PROFILE, None
-    by = {}
-    for name, flops, e0, e1 in rec:
+    by, shapes = {}, {}
+    for name, flops, e0, e1, tag in rec:
+        ms = e0.elapsed_time(e1)
         d = by.setdefault(name, dict(ms=0.0, flops=0.0, n=0))
-        d["ms"] += e0.elapsed_time(e1)
+        d["ms"] += ms
         d["flops"] += flops
         d["n"] += 1
+        if tag:
+            t = shapes.setdefault(tag, dict(ms=0.0, flops=0.0, n=0))
+            t["ms"] += ms
+            t["flops"] += flops
+            t["n"] += 1
+    if os.environ.get("IA2P_BENCH_SHAPES"):
+        for tag, t in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"]):
+            print(f"# {t['ms']:8.3f} ms  n={t['n']:3d}  {t['flops'] / max(t['ms'], 1e-9) / 1e9:7.1f} TFLOP/s  {tag}", file=sys.stderr)
     return by
 
 

@@ -98,6 +98,23 @@ int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64
                    const float* bias, const float* rowbias, int64_t rows_per_batch,
                    const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue, void* stream);
 
+/* ia2p_gemm_bf16 + LayerNorm folding (replaces [3P] BasicTransformerBlock.norm1/2/3 followed by to_q/k/v, attn2.to_q and
+ * the GEGLU projection -- SURVEY A.3 -- without a separate normalisation pass):
+ *   PRODUCER (a GEMM writing the fp32 residual stream): out_bf16 (row pitch ldo2) receives a bf16 copy of the output rows and
+ *     stats_out[M][ia2p_gemm_ln_parts(N)][2] the per-row partial (sum, sum of squares) of every column half-tile.
+ *   CONSUMER: A = those raw bf16 rows, W = bf16(W_linear * gamma) (host pre-scaled), ln_c1[n] = sum_k W[n,k], bias[n] must
+ *     already contain W_linear @ beta; the epilogue applies  rstd[m] * (acc - mean[m] * ln_c1[n]) + bias[n]  (before GEGLU)
+ *     with mean / rstd of row m reduced, in fixed order, from ln_stats[M][ln_parts][2]; normalised width = K1 + K2.
+ * All LN arguments are optional (NULL / 0): then this is exactly ia2p_gemm_bf16. */
+int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
+                      const void* W, void* out, int64_t ldo, int64_t M, int64_t N,
+                      const float* bias, const float* rowbias, int64_t rows_per_batch,
+                      const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue,
+                      void* out_bf16, int64_t ldo2, float* stats_out,
+                      const float* ln_stats, int64_t ln_parts, const float* ln_c1, float ln_eps, void* stream);
+/* number of (sum, sumsq) partials per row a producer with N output columns writes */
+int64_t ia2p_gemm_ln_parts(int64_t N);
+
 /* 3x3 conv (pad 1, stride 1|2) on NHWC bf16 as implicit GEMM, with an optional fused 1x1 shortcut conv
  * (extra K range) over up to two raw sources, bias, per-image channel bias (time embedding) and residual.
  * Replaces [3P] ResnetBlock2D.conv1 (+ time_emb_proj add), conv2 (+ conv_shortcut + residual add),

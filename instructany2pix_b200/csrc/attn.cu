@@ -185,120 +185,139 @@ cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv
   constexpr int TK = T1 + T2;
   constexpr int NT = TK / 8, NT1 = T1 / 8;
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sQ = smem_u32(smem);        // 128 x 64
-  const uint32_t sK = sQ + 128 * 128;        // TK x 64
+  const uint32_t sQ0 = smem_u32(smem);       // 2 x (128 x 64): double-buffered Q tiles
+  const uint32_t sK = sQ0 + 2 * 128 * 128;   // TK x 64
   const uint32_t sV = sK + TK * 128;         // TK x 64
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int q0 = blockIdx.x * 128;
   const int h = blockIdx.y;
   const long long b = blockIdx.z;
-  load_tile(sQ, q + (b * n_q + q0) * ldq + h * 64, ldq, 128, min(128, n_q - q0), tid, 256);
+  const int n_qtiles = (n_q + 127) >> 7;
+  // K/V of this (batch, head) are loaded ONCE per CTA; the CTA then walks its query tiles with the next Q tile in flight
   load_tile(sK, kt + b * n_text * ldkv + h * 64, ldkv, T1, n_text, tid, 256);
   load_tile(sV, vt + b * n_text * ldkv + h * 64, ldkv, T1, n_text, tid, 256);
   if (T2 > 0) {
     load_tile(sK + T1 * 128, ki + b * n_ip * ldkv_ip + h * 64, ldkv_ip, T2, n_ip, tid, 256);
     load_tile(sV + T1 * 128, vi + b * n_ip * ldkv_ip + h * 64, ldkv_ip, T2, n_ip, tid, 256);
   }
+  {
+    const int q0 = blockIdx.x * 128;
+    load_tile(sQ0, q + (b * n_q + q0) * ldq + h * 64, ldq, 128, min(128, n_q - q0), tid, 256);
+  }
   cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
 
-  uint32_t qf[4][4];
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-    ldsm_x4(sQ + tile_off(r, kk * 2 + (lane >> 4)), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
-  }
-  float s[NT][4];
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-    for (int kp = 0; kp < 2; ++kp) {
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), kp * 4 + (lane >> 3)), b0, b1, b2, b3);
-      mma_bf16(s[nt], qf[kp * 2], b0, b1);
-      mma_bf16(s[nt], qf[kp * 2 + 1], b2, b3);
+  int it = 0;
+  for (int qt = blockIdx.x; qt < n_qtiles; qt += gridDim.x, ++it) {
+    const int q0 = qt * 128;
+    const uint32_t sQ = sQ0 + (it & 1) * 128 * 128;
+    const int qn = qt + gridDim.x;
+    if (qn < n_qtiles) {                      // prefetch the next Q tile into the other buffer
+      load_tile(sQ0 + ((it + 1) & 1) * 128 * 128, q + (b * n_q + qn * 128) * ldq + h * 64, ldq, 128, min(128, n_q - qn * 128), tid, 256);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-  }
-  // two independent softmaxes: text keys [0, n_text) and IP keys [T1, T1 + n_ip)
-  float mx[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
+    __syncthreads();
+
+    uint32_t qf[4][4];
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int br = nt < NT1 ? 0 : 1;
-    const int lim = br == 0 ? n_text : n_ip;
-    const int kidx = (br == 0 ? nt * 8 : nt * 8 - T1) + 2 * t;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const bool ok = kidx + e < lim;
-      s[nt][e] = ok ? s[nt][e] * scale_log2 : -INFINITY;
-      s[nt][2 + e] = ok ? s[nt][2 + e] * scale_log2 : -INFINITY;
-      mx[br][0] = fmaxf(mx[br][0], s[nt][e]);
-      mx[br][1] = fmaxf(mx[br][1], s[nt][2 + e]);
+    for (int kk = 0; kk < 4; ++kk) {
+      const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      ldsm_x4(sQ + tile_off(r, kk * 2 + (lane >> 4)), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
     }
-  }
-  float sum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    float s[NT][4];
 #pragma unroll
-  for (int br = 0; br < 2; ++br)
+    for (int nt = 0; nt < NT; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[br][r] = fmaxf(mx[br][r], __shfl_xor_sync(0xffffffffu, mx[br][r], 1));
-      mx[br][r] = fmaxf(mx[br][r], __shfl_xor_sync(0xffffffffu, mx[br][r], 2));
-      if (mx[br][r] == -INFINITY) mx[br][r] = 0.f;   // empty branch (n_ip == 0): exp2(-inf - 0) = 0
+      for (int kp = 0; kp < 2; ++kp) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), kp * 4 + (lane >> 3)), b0, b1, b2, b3);
+        mma_bf16(s[nt], qf[kp * 2], b0, b1);
+        mma_bf16(s[nt], qf[kp * 2 + 1], b2, b3);
+      }
     }
+    // two independent softmaxes: text keys [0, n_text) and IP keys [T1, T1 + n_ip)
+    float mx[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int br = nt < NT1 ? 0 : 1;
-    s[nt][0] = exp2f(s[nt][0] - mx[br][0]); s[nt][1] = exp2f(s[nt][1] - mx[br][0]);
-    s[nt][2] = exp2f(s[nt][2] - mx[br][1]); s[nt][3] = exp2f(s[nt][3] - mx[br][1]);
-    sum[br][0] += s[nt][0] + s[nt][1];
-    sum[br][1] += s[nt][2] + s[nt][3];
-  }
-  float w[2][2];
+    for (int nt = 0; nt < NT; ++nt) {
+      const int br = nt < NT1 ? 0 : 1;
+      const int lim = br == 0 ? n_text : n_ip;
+      const int kidx = (br == 0 ? nt * 8 : nt * 8 - T1) + 2 * t;
 #pragma unroll
-  for (int br = 0; br < 2; ++br)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      sum[br][r] += __shfl_xor_sync(0xffffffffu, sum[br][r], 1);
-      sum[br][r] += __shfl_xor_sync(0xffffffffu, sum[br][r], 2);
-      const float inv = sum[br][r] > 0.f ? 1.f / sum[br][r] : 0.f;
-      w[br][r] = br == 0 ? inv : inv * ip_scale;
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = kidx + e < lim;
+        s[nt][e] = ok ? s[nt][e] * scale_log2 : -INFINITY;
+        s[nt][2 + e] = ok ? s[nt][2 + e] * scale_log2 : -INFINITY;
+        mx[br][0] = fmaxf(mx[br][0], s[nt][e]);
+        mx[br][1] = fmaxf(mx[br][1], s[nt][2 + e]);
+      }
     }
-  float o[8][4];
+    float sum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    for (int br = 0; br < 2; ++br)
 #pragma unroll
-  for (int kk = 0; kk < TK / 16; ++kk) {
-    const int br = (2 * kk) < NT1 ? 0 : 1;      // T1 is a multiple of 16: a 16-key step never straddles branches
-    uint32_t pa[4];
-    pa[0] = pack_bf16x2(s[2 * kk][0] * w[br][0], s[2 * kk][1] * w[br][0]);
-    pa[1] = pack_bf16x2(s[2 * kk][2] * w[br][1], s[2 * kk][3] * w[br][1]);
-    pa[2] = pack_bf16x2(s[2 * kk + 1][0] * w[br][0], s[2 * kk + 1][1] * w[br][0]);
-    pa[3] = pack_bf16x2(s[2 * kk + 1][2] * w[br][1], s[2 * kk + 1][3] * w[br][1]);
+      for (int r = 0; r < 2; ++r) {
+        mx[br][r] = fmaxf(mx[br][r], __shfl_xor_sync(0xffffffffu, mx[br][r], 1));
+        mx[br][r] = fmaxf(mx[br][r], __shfl_xor_sync(0xffffffffu, mx[br][r], 2));
+        if (mx[br][r] == -INFINITY) mx[br][r] = 0.f;   // empty branch (n_ip == 0): exp2(-inf - 0) = 0
+      }
 #pragma unroll
-    for (int dp = 0; dp < 4; ++dp) {
-      uint32_t b0, b1, b2, b3;
-      const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      ldsm_x4_t(sV + tile_off(r, dp * 2 + (lane >> 4)), b0, b1, b2, b3);
-      mma_bf16(o[2 * dp], pa, b0, b1);
-      mma_bf16(o[2 * dp + 1], pa, b2, b3);
+    for (int nt = 0; nt < NT; ++nt) {
+      const int br = nt < NT1 ? 0 : 1;
+      s[nt][0] = ex2_approx(s[nt][0] - mx[br][0]); s[nt][1] = ex2_approx(s[nt][1] - mx[br][0]);
+      s[nt][2] = ex2_approx(s[nt][2] - mx[br][1]); s[nt][3] = ex2_approx(s[nt][3] - mx[br][1]);
+      sum[br][0] += s[nt][0] + s[nt][1];
+      sum[br][1] += s[nt][2] + s[nt][3];
     }
-  }
-  __syncwarp();
-  uint8_t* sq = smem;
+    float w[2][2];
 #pragma unroll
-  for (int dt = 0; dt < 8; ++dt) {
-    const int r0 = warp * 16 + g, r1 = r0 + 8;
-    *reinterpret_cast<uint32_t*>(sq + tile_off(r0, dt) + t * 4) = pack_bf16x2(o[dt][0], o[dt][1]);
-    *reinterpret_cast<uint32_t*>(sq + tile_off(r1, dt) + t * 4) = pack_bf16x2(o[dt][2], o[dt][3]);
-  }
-  __syncwarp();
-  __nv_bfloat16* og = out + (b * n_q + q0) * ldo + h * 64;
-  for (int id = lane; id < 16 * 8; id += 32) {
-    const int r = warp * 16 + (id >> 3), ch = id & 7;
-    if (q0 + r < n_q)
-      *reinterpret_cast<uint4*>(og + (long long)r * ldo + ch * 8) = *reinterpret_cast<const uint4*>(sq + tile_off(r, ch));
+    for (int br = 0; br < 2; ++br)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        sum[br][r] += __shfl_xor_sync(0xffffffffu, sum[br][r], 1);
+        sum[br][r] += __shfl_xor_sync(0xffffffffu, sum[br][r], 2);
+        const float inv = sum[br][r] > 0.f ? 1.f / sum[br][r] : 0.f;
+        w[br][r] = br == 0 ? inv : inv * ip_scale;
+      }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < TK / 16; ++kk) {
+      const int br = (2 * kk) < NT1 ? 0 : 1;      // T1 is a multiple of 16: a 16-key step never straddles branches
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0] * w[br][0], s[2 * kk][1] * w[br][0]);
+      pa[1] = pack_bf16x2(s[2 * kk][2] * w[br][1], s[2 * kk][3] * w[br][1]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0] * w[br][0], s[2 * kk + 1][1] * w[br][0]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2] * w[br][1], s[2 * kk + 1][3] * w[br][1]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldsm_x4_t(sV + tile_off(r, dp * 2 + (lane >> 4)), b0, b1, b2, b3);
+        mma_bf16(o[2 * dp], pa, b0, b1);
+        mma_bf16(o[2 * dp + 1], pa, b2, b3);
+      }
+    }
+    // stage this warp's 16 x 64 tile through its own rows of the (consumed) Q buffer for 16-byte coalesced stores
+    __syncwarp();
+    uint8_t* sq = smem + (it & 1) * 128 * 128;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int r0 = warp * 16 + g, r1 = r0 + 8;
+      *reinterpret_cast<uint32_t*>(sq + tile_off(r0, dt) + t * 4) = pack_bf16x2(o[dt][0], o[dt][1]);
+      *reinterpret_cast<uint32_t*>(sq + tile_off(r1, dt) + t * 4) = pack_bf16x2(o[dt][2], o[dt][3]);
+    }
+    __syncwarp();
+    __nv_bfloat16* og = out + (b * n_q + q0) * ldo + h * 64;
+    for (int id = lane; id < 16 * 8; id += 32) {
+      const int r = warp * 16 + (id >> 3), ch = id & 7;
+      if (q0 + r < n_q)
+        *reinterpret_cast<uint4*>(og + (long long)r * ldo + ch * 8) = *reinterpret_cast<const uint4*>(sq + tile_off(r, ch));
+    }
+    __syncthreads();      // buffer (it & 1) is refilled by the prefetch issued at the top of the next iteration
   }
 }
 
@@ -306,13 +325,18 @@ template <int T1, int T2>
 static int launch_cross(const void* q, int64_t ldq, const void* kt, const void* vt, int64_t ldkv, int n_text, const void* ki,
                         const void* vi, int64_t ldkv_ip, int n_ip, float ip_scale, void* out, int64_t ldo, int64_t batch,
                         int64_t n_q, int heads, float scale, cudaStream_t st) {
-  constexpr int smem = 128 * 128 + 2 * (T1 + T2) * 128;
+  constexpr int smem = 2 * 128 * 128 + 2 * (T1 + T2) * 128;
   static bool done = false;
   if (!done) {
     IA2P_CUDA(cudaFuncSetAttribute(cross_attn_kernel<T1, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     done = true;
   }
-  const dim3 grid((unsigned)((n_q + 127) / 128), (unsigned)heads, (unsigned)batch);
+  // query tiles per (batch, head) are split over the fewest CTAs that still fill the GPU (~3 CTAs per SM): K/V loads amortise
+  const int n_qtiles = (int)((n_q + 127) / 128);
+  int split = n_qtiles;
+  for (int d = 1; d <= n_qtiles; ++d)
+    if (n_qtiles % d == 0 && (long long)d * heads * batch >= 3LL * sm_count()) { split = d; break; }
+  const dim3 grid((unsigned)split, (unsigned)heads, (unsigned)batch);
   cross_attn_kernel<T1, T2><<<grid, 256, smem, st>>>(
       static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(kt), static_cast<const __nv_bfloat16*>(vt),
       ldkv, n_text, static_cast<const __nv_bfloat16*>(ki), static_cast<const __nv_bfloat16*>(vi), ldkv_ip, n_ip, ip_scale,

@@ -44,6 +44,16 @@ struct TcParams {
   void* out;                       // bf16 or fp32 (out_f32)
   long long ldo, ldr;
   int geglu, out_f32, res_f32;
+  // LayerNorm folding: a PRODUCER of the fp32 residual stream also emits a bf16 copy of its output rows and
+  // per-row partial (sum, sum of squares) over each column half of every N tile; a CONSUMER multiplies the raw bf16 rows
+  // by gamma-scaled weights and finishes LN in its epilogue: rstd[m] * (acc - mean[m] * c1[n]) + c2[n].
+  __nv_bfloat16* out2;             // producer: bf16 copy of out (row pitch ldo2) | NULL
+  long long ldo2;
+  float* stats_out;                // producer: [rows][2 * n_tiles][2] partial sums | NULL
+  const float* ln_stats;           // consumer: [rows][ln_parts][2] | NULL
+  const float* ln_c1;              // consumer: [N]  (row sums of the gamma-scaled weight)
+  int ln_parts;
+  float ln_inv_n, ln_eps;          // 1 / (normalised width), epsilon
 };
 
 // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BLOCK_N tile:
@@ -220,6 +230,20 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const float* rb = (p.rowbias != nullptr && valid) ? p.rowbias + (pix / p.rows_per_batch) * (long long)p.N : nullptr;
       const bool res32 = (p.residual != nullptr) && p.res_f32 && valid && !p.geglu;
       const float* res_row = static_cast<const float*>(p.residual) + pix * p.ldr;
+      // consumer side of the LN fold: this row's mean / rstd from the producer's partial sums (fixed order: reproducible)
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats != nullptr && valid) {
+        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + pix * p.ln_parts;
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < p.ln_parts; ++i) {
+          const float2 v = __ldg(sp + i);
+          s1 += v.x;
+          s2 += v.y;
+        }
+        ln_mean = s1 * p.ln_inv_n;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_n - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
+      float st_sum = 0.f, st_sq = 0.f;                      // producer side: partial row statistics of this column half
 
       float rpre[2][32];
       auto load_res = [&](int c, float (&dst)[32]) {
@@ -231,6 +255,25 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       if (res32) {
         load_res(c_lo, rpre[0]);
         if (c_lo + 1 < c_hi) load_res(c_lo + 1, rpre[1]);
+      }
+      // pull the NEXT tile's residual rows (this warp's column half) from DRAM into L2 while this tile is processed: the
+      // epilogue of residual GEMMs with short K is latency-bound on these reads otherwise
+      if ((p.residual != nullptr) && p.res_f32 && !p.geglu && tile + unit_step < total_tiles) {
+        const int tile2 = tile + unit_step;
+        const int m_unit2 = tile2 / p.n_tiles, n_tile2 = tile2 - m_unit2 * p.n_tiles;
+        const int m_tile2 = m_unit2 * CG + (int)rank;
+        const int xt2 = m_tile2 % p.tiles_x;
+        const int r2 = m_tile2 / p.tiles_x;
+        const int yt2 = r2 % p.tiles_y, bt2 = r2 / p.tiles_y;
+        const int x2 = (xt2 << p.tw_log2) + tw, y2 = (yt2 << p.th_log2) + th, b2 = bt2 * TB + tb;
+        if ((x2 < p.Wo) && (y2 < p.Ho) && (b2 < p.B) && (m_tile2 < p.m_tiles)) {
+          const long long pix2 = ((long long)b2 * p.Ho + y2) * p.Wo + x2;
+          const float* rrow = static_cast<const float*>(p.residual) + pix2 * p.ldr + n_tile2 * BLOCK_N + c_lo * 32;
+#pragma unroll
+          for (int i = 0; i < (NCH0 * 32 * 4) / 128; ++i)
+            if (n_tile2 * BLOCK_N + c_lo * 32 + i * 32 < p.N)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + i * 32));
+        }
       }
 
       mbar_wait(tfull_bar(buf), use & 1u);
@@ -250,6 +293,14 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               float f[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+              if (p.ln_stats != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + i));
+                  f[i] = ln_rstd * (f[i] - ln_mean * cv.x); f[i + 1] = ln_rstd * (f[i + 1] - ln_mean * cv.y);
+                  f[i + 2] = ln_rstd * (f[i + 2] - ln_mean * cv.z); f[i + 3] = ln_rstd * (f[i + 3] - ln_mean * cv.w);
+                }
+              }
               if (p.bias != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -281,6 +332,20 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     t = unpack_bf16x2(rv.z); f[8 * i + 4] += t.x; f[8 * i + 5] += t.y;
                     t = unpack_bf16x2(rv.w); f[8 * i + 6] += t.x; f[8 * i + 7] += t.y;
                   }
+                }
+              }
+              if (p.stats_out != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { st_sum += f[i]; st_sq += f[i] * f[i]; }
+              }
+              if (p.out2 != nullptr) {
+                __nv_bfloat16* op2 = p.out2 + pix * p.ldo2 + n;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  float o[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(pack_bf16x2(f[16 * i + 2 * k], f[16 * i + 2 * k + 1]));
+                  stg256(reinterpret_cast<float*>(op2 + i * 16), o);
                 }
               }
               if (p.out_f32) {
@@ -319,10 +384,20 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
                 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32 + i));
               }
-              f[i + 0] = (__uint_as_float(vv[i + 0]) + bv.x) * gelu_erf_f(__uint_as_float(vg[i + 0]) + bg.x);
-              f[i + 1] = (__uint_as_float(vv[i + 1]) + bv.y) * gelu_erf_f(__uint_as_float(vg[i + 1]) + bg.y);
-              f[i + 2] = (__uint_as_float(vv[i + 2]) + bv.z) * gelu_erf_f(__uint_as_float(vg[i + 2]) + bg.z);
-              f[i + 3] = (__uint_as_float(vv[i + 3]) + bv.w) * gelu_erf_f(__uint_as_float(vg[i + 3]) + bg.w);
+              float a0 = __uint_as_float(vv[i + 0]), a1 = __uint_as_float(vv[i + 1]), a2 = __uint_as_float(vv[i + 2]), a3 = __uint_as_float(vv[i + 3]);
+              float g0 = __uint_as_float(vg[i + 0]), g1 = __uint_as_float(vg[i + 1]), g2 = __uint_as_float(vg[i + 2]), g3 = __uint_as_float(vg[i + 3]);
+              if (p.ln_stats != nullptr) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + i));
+                const float4 cg = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + 32 + i));
+                a0 = ln_rstd * (a0 - ln_mean * cv.x); a1 = ln_rstd * (a1 - ln_mean * cv.y);
+                a2 = ln_rstd * (a2 - ln_mean * cv.z); a3 = ln_rstd * (a3 - ln_mean * cv.w);
+                g0 = ln_rstd * (g0 - ln_mean * cg.x); g1 = ln_rstd * (g1 - ln_mean * cg.y);
+                g2 = ln_rstd * (g2 - ln_mean * cg.z); g3 = ln_rstd * (g3 - ln_mean * cg.w);
+              }
+              f[i + 0] = (a0 + bv.x) * gelu_erf_f(g0 + bg.x);
+              f[i + 1] = (a1 + bv.y) * gelu_erf_f(g1 + bg.y);
+              f[i + 2] = (a2 + bv.z) * gelu_erf_f(g2 + bg.z);
+              f[i + 3] = (a3 + bv.w) * gelu_erf_f(g3 + bg.w);
             }
             __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + (n >> 1);
 #pragma unroll
@@ -335,6 +410,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         }
       }
+      if (p.stats_out != nullptr && valid)
+        *reinterpret_cast<float2*>(p.stats_out + ((pix * p.n_tiles + n_tile) * 2 + half) * 2) = make_float2(st_sum, st_sq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -480,7 +557,25 @@ extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void
                               const void* W, void* out, int64_t ldo, int64_t M, int64_t N,
                               const float* bias, const float* rowbias, int64_t rows_per_batch,
                               const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue, void* stream) {
+  return ia2p_gemm_ln_bf16(A, lda, K1, A2, lda2, K2, W, out, ldo, M, N, bias, rowbias, rows_per_batch, residual, ldr, res_dtype,
+                           out_dtype, epilogue, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, stream);
+}
+
+extern "C" int64_t ia2p_gemm_ln_parts(int64_t N) { return 2 * ((N + pick_block_n(N, false) - 1) / pick_block_n(N, false)); }
+
+extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
+                                 const void* W, void* out, int64_t ldo, int64_t M, int64_t N,
+                                 const float* bias, const float* rowbias, int64_t rows_per_batch,
+                                 const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue,
+                                 void* out_bf16, int64_t ldo2, float* stats_out,
+                                 const float* ln_stats, int64_t ln_parts, const float* ln_c1, float ln_eps, void* stream) {
   if (int e = check_device()) return e;
+  IA2P_REQUIRE((ln_stats == nullptr) == (ln_c1 == nullptr) && (ln_stats == nullptr || (ln_parts > 0 && ln_parts <= 64)), IA2P_E_ARG,
+               "gemm: ln_stats, ln_c1 and ln_parts must be given together");
+  IA2P_REQUIRE((out_bf16 == nullptr && stats_out == nullptr) || epilogue != IA2P_EPI_GEGLU, IA2P_E_ARG,
+               "gemm: the GEGLU epilogue cannot also produce LN statistics");
+  IA2P_REQUIRE(out_bf16 == nullptr || ((reinterpret_cast<uintptr_t>(out_bf16) & 31) == 0 && ldo2 % 16 == 0), IA2P_E_ALIGN,
+               "gemm: out_bf16 must be 32-byte aligned with ldo2 %% 16 == 0");
   IA2P_REQUIRE(A && W && out && M > 0 && N > 0 && K1 > 0, IA2P_E_ARG, "gemm: null pointer or empty shape");
   IA2P_REQUIRE((out_dtype == IA2P_BF16 || out_dtype == IA2P_F32) && (residual == nullptr || res_dtype == IA2P_BF16 || res_dtype == IA2P_F32),
                IA2P_E_ARG, "gemm: out/residual dtype must be bf16 or f32");
@@ -532,6 +627,9 @@ extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void
   p.out = out;
   p.ldo = ldo; p.ldr = ldr; p.geglu = geglu ? 1 : 0;
   p.out_f32 = out_dtype == IA2P_F32; p.res_f32 = res_dtype == IA2P_F32;
+  p.out2 = static_cast<__nv_bfloat16*>(out_bf16); p.ldo2 = ldo2; p.stats_out = stats_out;
+  p.ln_stats = ln_stats; p.ln_c1 = ln_c1; p.ln_parts = (int)ln_parts;
+  p.ln_inv_n = 1.0f / (float)(K1 + K2); p.ln_eps = ln_eps;
   return dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream));
 }
 

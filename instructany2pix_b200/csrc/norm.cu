@@ -36,7 +36,7 @@ template <> struct Vec8<float> {
 constexpr int kGnMaxSlabs = 128;
 
 template <typename T>
-__global__ void gn_stats_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
+__global__ void __launch_bounds__(512, 2) gn_stats_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
                                 long long hw, int groups, int pix_per_slab, double* __restrict__ partials) {
   extern __shared__ float sm[];   // [ROWS][2][C]
   const int C = ca + cb;
@@ -93,7 +93,7 @@ __global__ void gn_stats_kernel(const T* __restrict__ xa, int ca, const T* __res
 
 // ---------------------------------------------------------------- GroupNorm apply (+SiLU)
 template <typename T>
-__global__ void gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
+__global__ void __launch_bounds__(512, 2) gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw, long long hw, int groups,
                                 float eps, int silu, int pix_per_slab, const double* __restrict__ partials) {
@@ -161,13 +161,11 @@ __global__ void gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __res
   {
     const long long step = blockDim.y;
     long long p = p_begin + threadIdx.y;
-    for (; p + 3 * step < p_end; p += 4 * step) {
-      float f0[8], f1[8], f2[8], f3[8];
+    for (; p + step < p_end; p += 2 * step) {              // 2 independent loads in flight (register budget: 2 CTAs/SM)
+      float f0[8], f1[8];
       Vec8<T>::load(src + p * ld, f0);
       Vec8<T>::load(src + (p + step) * ld, f1);
-      Vec8<T>::load(src + (p + 2 * step) * ld, f2);
-      Vec8<T>::load(src + (p + 3 * step) * ld, f3);
-      emit(p, f0); emit(p + step, f1); emit(p + 2 * step, f2); emit(p + 3 * step, f3);
+      emit(p, f0); emit(p + step, f1);
     }
     for (; p < p_end; p += step) {
       float f[8];

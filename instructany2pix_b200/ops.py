@@ -24,10 +24,11 @@ LAUNCHES = 0
 PROFILE = None
 _KERNELS_PER_CALL = {"ia2p_groupnorm_nhwc": 2}
 _FLOPS = 0.0
+_TAG = ""
 
 
 def _run(fn, args, what):
-    global LAUNCHES, _FLOPS
+    global LAUNCHES, _FLOPS, _TAG
     LAUNCHES += _KERNELS_PER_CALL.get(fn.__name__, 1)
     prof = PROFILE
     if prof is not None:
@@ -35,10 +36,11 @@ def _run(fn, args, what):
         e0.record()
         status = fn(*args)
         e1.record()
-        prof.append((fn.__name__, _FLOPS, e0, e1))
+        prof.append((fn.__name__, _FLOPS, e0, e1, _TAG))
     else:
         status = fn(*args)
     _FLOPS = 0.0
+    _TAG = ""
     if status != 0:
         _lib.check(status, what)
 
@@ -200,9 +202,13 @@ def layernorm(x, gamma, beta, eps, out_dtype=None):
 
 # ------------------------------------------------------------------------------------------------ tensor-core GEMM / conv
 def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None, geglu=False, out=None,
-         out_dtype=torch.bfloat16):
+         out_dtype=torch.bfloat16, want_ln=False, ln=None):
     """out = epilogue([a | a2] @ w^T).  a: [M,K1] bf16 (row-strided view allowed), w: [N,K1+K2] bf16 contiguous;
-    residual bf16|fp32, out bf16|fp32 (fp32 = residual-stream tensors)."""
+    residual bf16|fp32, out bf16|fp32 (fp32 = residual-stream tensors).
+
+    LayerNorm folding: ``want_ln=True`` (producer) returns ``(out, out_bf16, stats)`` -- a bf16 copy of the output rows and
+    the per-row partial sums; ``ln=(stats, c1, eps)`` (consumer) finishes LayerNorm in the epilogue:
+    ``rstd * (a @ w^T - mean * c1) + bias`` with ``w`` pre-scaled by gamma and ``bias`` already holding ``W @ beta``."""
     lib = _lib.load()
     _need(a, torch.bfloat16, "a", 2)
     _need(w, torch.bfloat16, "w", 2)
@@ -229,11 +235,30 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
         assert residual.shape == (M, n_out) and residual.dtype in (torch.bfloat16, torch.float32)
         ldr, res_dt = _rows(residual, "residual"), _DT[residual.dtype]
     bias, rowbias = _f32(bias, "bias"), _f32(rowbias, "rowbias")
-    global _FLOPS
+    out2 = stats = None
+    if want_ln:
+        assert not geglu
+        out2 = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+        stats = torch.empty(M, int(lib.ia2p_gemm_ln_parts(N)), 2, device=a.device, dtype=torch.float32)
+    ln_stats = ln_c1 = None
+    ln_parts, ln_eps = 0, 0.0
+    if ln is not None:
+        ln_stats, ln_c1, ln_eps = ln
+        ln_stats, ln_c1 = _f32(ln_stats, "ln_stats"), _f32(ln_c1, "ln_c1")
+        assert ln_stats.shape[0] == M and ln_c1.numel() == N
+        ln_parts = ln_stats.shape[1]
+    global _FLOPS, _TAG
     _FLOPS = 2.0 * M * N * (K1 + K2)
-    _run(lib.ia2p_gemm_bf16, (a.data_ptr(), lda, K1, _ptr(a2), lda2, K2, w.data_ptr(), out.data_ptr(), ldo, M, N,
+    if PROFILE is not None:
+        _TAG = (f"gemm M{M} N{N} K{K1 + K2}{' geglu' if geglu else ''}{' res' + str(residual.dtype)[6:] if residual is not None else ''}"
+                f" out{str(out.dtype)[6:]}{' +ln_stats' if want_ln else ''}{' ln_fold' if ln is not None else ''}")
+    _run(lib.ia2p_gemm_ln_bf16, (a.data_ptr(), lda, K1, _ptr(a2), lda2, K2, w.data_ptr(), out.data_ptr(), ldo, M, N,
                                   _ptr(bias), _ptr(rowbias), int(rows_per_batch), _ptr(residual), ldr, res_dt,
-                                  _DT[out.dtype], _lib.EPI_GEGLU if geglu else _lib.EPI_NONE, _stream()), "gemm_bf16")
+                                  _DT[out.dtype], _lib.EPI_GEGLU if geglu else _lib.EPI_NONE,
+                                  _ptr(out2), N, _ptr(stats), _ptr(ln_stats), ln_parts, _ptr(ln_c1), float(ln_eps),
+                                  _stream()), "gemm_bf16")
+    if want_ln:
+        return out, out2, stats
     return out
 
 
@@ -263,8 +288,10 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
         assert residual.shape == out.shape and residual.dtype in (torch.bfloat16, torch.float32)
         res_dt = _DT[residual.dtype]
     bias, rowbias = _f32(bias, "bias"), _f32(rowbias, "rowbias")
-    global _FLOPS
+    global _FLOPS, _TAG
     _FLOPS = 2.0 * B * Ho * Wo * cout * w.shape[1]
+    if PROFILE is not None:
+        _TAG = f"conv {H}x{W} C{Cin}->{cout} K{w.shape[1]} s{stride}{' res' if residual is not None else ''} out{str(out_dtype)[6:]}"
     _run(lib.ia2p_conv3x3_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, stride, w.data_ptr(), _ptr(sc_a), ca, _ptr(sc_b), cb,
                                           out.data_ptr(), _DT[out_dtype], cout, _ptr(bias), _ptr(rowbias), _ptr(residual),
                                           res_dt, _stream()), "conv3x3")

@@ -97,10 +97,17 @@ def layernorm(x, gamma, beta, eps, out_dtype=None):
     return F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps).to(out_dtype or x.dtype)
 
 
-def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None, geglu=False, out=None, out_dtype=BF):
+def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None, geglu=False, out=None, out_dtype=BF,
+         want_ln=False, ln=None):
     assert a.dtype == BF and w.dtype == BF
     A = a.float() if a2 is None else torch.cat([a, a2], 1).float()
     h = A @ w.float().t()
+    if ln is not None:                                  # consumer side of the LayerNorm fold
+        stats, c1, eps = ln
+        s = stats.sum(1)
+        mean = s[:, 0:1] / A.shape[1]
+        rstd = torch.rsqrt((s[:, 1:2] / A.shape[1] - mean * mean).clamp_min(0) + eps)
+        h = rstd * (h - mean * c1[None])
     if bias is not None:
         h = h + bias
     if rowbias is not None:
@@ -111,6 +118,11 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
         h = (hv[:, :, 0] * F.gelu(hv[:, :, 1])).reshape(-1, n // 2)
     if residual is not None:
         h = h + residual.float()
+    if want_ln:                                         # producer side: bf16 copy + per-row partial sums (2 parts here)
+        half = h.shape[1] // 2
+        stats = torch.stack([torch.stack([h[:, :half].sum(1), (h[:, :half] ** 2).sum(1)], -1),
+                             torch.stack([h[:, half:].sum(1), (h[:, half:] ** 2).sum(1)], -1)], 1)
+        return h.to(out_dtype), h.to(BF), stats
     h = h.to(out_dtype)
     if out is not None:
         out.copy_(h)

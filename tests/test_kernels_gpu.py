@@ -61,6 +61,34 @@ def test_gemm_fp32_stream():
     assert out2.dtype == torch.bfloat16 and rel(out2, a.float() @ w.float().t() + res) < TOL
 
 
+@pytest.mark.parametrize("M,C,N,geglu", [(512, 1280, 3840, False), (1000, 640, 640, False), (384, 640, 5120, True), (256, 128, 192, False)])
+def test_gemm_layernorm_fold(M, C, N, geglu):
+    """producer (fp32 stream + bf16 copy + row statistics) -> consumer (LayerNorm finished in the epilogue)."""
+    from instructany2pix_b200.packing import interleave_geglu
+    from instructany2pix_b200.unet import _fold_ln
+    a0, w0 = rnd(M, 256), rnd(C, 256, scale=256 ** -0.5)
+    res = rnd(M, C, dtype=torch.float32, scale=2.0) + 0.7          # non-zero row means
+    t, tb, st = ops.gemm(a0, w0, residual=res, out_dtype=torch.float32, want_ln=True)
+    t_ref = a0.float() @ w0.float().t() + res
+    assert rel(t, t_ref) < 2e-6 and torch.equal(tb, t.to(torch.bfloat16))
+    assert rel(st.sum(1)[:, 0], t.sum(1)) < 1e-5 and rel(st.sum(1)[:, 1], (t * t).sum(1)) < 1e-5
+    ln = torch.nn.LayerNorm(C, eps=1e-5).to(DEV)
+    ln.weight.data = rnd(C, dtype=torch.float32) * 0.3 + 1.0
+    ln.bias.data = rnd(C, dtype=torch.float32) * 0.2
+    w = rnd(N, C, scale=C ** -0.5)
+    b = rnd(N, dtype=torch.float32, scale=0.1)
+    if geglu:
+        w, b = interleave_geglu(w, b)
+    wp, c1, c2, eps = _fold_ln(w, b, ln)
+    out = ops.gemm(tb, wp, bias=c2, ln=(st, c1, eps), geglu=geglu)
+    h = F.layer_norm(t, (C,), ln.weight, ln.bias, 1e-5) @ w.float().t() + b
+    if geglu:
+        hv = h.reshape(M, N // 64, 2, 32)
+        h = (hv[:, :, 0] * F.gelu(hv[:, :, 1])).reshape(M, N // 2)
+    # vs exact fp32 LayerNorm + Linear: operand rounding (raw rows and gamma-scaled weights in bf16) ~ 2^-8
+    assert rel(out, h) < 8e-3
+
+
 def test_gemm_k_concat_and_strided_views():
     M, K1, K2, N = 640, 128, 192, 320
     big = rnd(M, 512)

@@ -89,3 +89,21 @@ def test_sampler_parity(graph):
     ref_i = osampler.invert(o, lat, ctx[2:, :77], {k: v[2:] for k, v in added.items()}, num_inference_steps=4)
     out_i = s.invert(cu(lat), cu(ctx[2:, :77]), cu({k: v[2:] for k, v in added.items()}), num_inference_steps=4)
     assert rel(out_i.cpu(), ref_i) < 2e-2
+
+
+def test_decoded_image_psnr():
+    """North-star gate: free-running trajectory -> decode both final latents with the SAME (oracle) VAE decoder -> PSNR >= 35 dB."""
+    from oracle.synth import synth_state_dict
+    from oracle.vae import TINY_VAE, OracleVAEDecoder, psnr
+    o, b = build_pair(True, device="cuda")
+    lat, ctx, added = make_inputs(TINY, B=2, L=16)
+    ref = osampler.generate(o, lat, ctx, added, num_inference_steps=10, guidance_scale=7.5)
+    out = B200Sampler(b).generate(cu(lat), cu(ctx), cu(added), num_inference_steps=10, guidance_scale=7.5).cpu()
+    vae = OracleVAEDecoder(TINY_VAE).eval()
+    vae.load_state_dict(synth_state_dict(vae, 11))
+    img_ref, img_out = vae.decode(ref), vae.decode(out)
+    # normalise the (random-weight) decoder's output range to the nominal [-1, 1] image range before measuring
+    s = img_ref.abs().max().clamp_min(1e-6)
+    db = psnr(img_out / s, img_ref / s)
+    print(f"decoded-image PSNR (10 free-running steps): {db:.1f} dB; latent rel-L2 {rel(out, ref):.2e}")
+    assert db >= 35.0
