@@ -28,6 +28,9 @@ constexpr int kMaxTaps = 24;
 struct alignas(64) TcMaps {
   CUtensorMap a[4];
   CUtensorMap w;
+  CUtensorMap w2;                  // same matrix, box of HALF the rows: the B operand of a tail-split half tile
+  CUtensorMap o, o2;               // EPI >= 1: fp32 output / bf16 copy, boxes of 16 columns x the 128 tile pixels
+  CUtensorMap r;                   // EPI == 2: fp32 residual, same boxes
 };
 
 struct TcParams {
@@ -35,6 +38,9 @@ struct TcParams {
   int ntaps, num_kb;
   int tw_log2, th_log2;            // M tile = TB x TH x TW output pixels, TB*TH*TW == 128
   int tiles_x, tiles_y, m_tiles, n_tiles;
+  // Tail split (wave quantisation): work items [0, full_items) are whole 128 x BLOCK_N tiles; the remaining tiles -- the
+  // ones that would form a last, mostly idle wave -- are cut into `split` column slices each, so that every SM gets a slice.
+  int full_items, total_items, split;
   int Wo, Ho, B;                   // output pixel grid (plain GEMM: Wo = M, Ho = B = 1)
   int N;                           // GEMM N (pre-GEGLU)
   int rows_per_batch;              // rowbias row = pixel / rows_per_batch
@@ -56,30 +62,61 @@ struct TcParams {
   float ln_inv_n, ln_eps;          // 1 / (normalised width), epsilon
 };
 
+struct TcItem { int m_unit, n_tile, n_off, w; };
+__device__ __forceinline__ TcItem tc_decode_item(const TcParams& p, int item, int block_n) {
+  TcItem it;
+  int tile = item;
+  it.n_off = 0;
+  it.w = block_n;
+  if (item >= p.full_items) {                 // split is 1 or 2
+    const int j = item - p.full_items;
+    tile = p.full_items + (j >> 1);
+    it.w = block_n >> 1;
+    it.n_off = (j & 1) * it.w;
+  }
+  it.m_unit = tile / p.n_tiles;
+  it.n_tile = tile - it.m_unit * p.n_tiles;
+  return it;
+}
+
 // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BLOCK_N tile:
 // each CTA stages its own 128 A rows and HALF of the B rows, so the per-SM shared-memory traffic per MMA cycle drops by a
 // third -- with CG = 1 the UMMA operand reads + TMA writes (192 B/clk at 128x256x64) exceed what smem sustains and cap the
 // main loop near 55 % of the tensor peak (measured, profiles/README.md).
-template <int BLOCK_N, int CG = 1>
+//
+// EPI = 0: the epilogue stores straight from registers (bf16 outputs: 64 KB per tile, far below what the LSU path moves).
+// EPI = 1 (fp32 outputs, optionally + bf16 copy: 192 KB per tile): thread-per-row register stores top out near 23 GB/s per
+// SM (tools/membench.cu: one sector per lane per instruction), which made the fp32 residual GEMMs epilogue-bound.  Here the
+// two epilogue half-groups (4 warps = 128 rows each) stage 16-column slices in swizzled shared memory and one elected
+// thread per half-group hands them to the TMA store engine.
+// EPI = 2 (fp32 residual GEMMs with a short K: attention out-projections): additionally the residual slices arrive by TMA
+// load, two chunks ahead, into a 4-deep ring of the same staging slices (the thread reads its row, adds, and writes the
+// result back in place); the main loop gives up one stage for the ring.  With register loads the residual reads (a sector
+// per lane per instruction, 2 chunks of prefetch) were the critical path of those GEMMs (profiles/README.md).
+template <int BLOCK_N, int CG = 1, int EPI = 0>
 struct TcCfg {
   static constexpr int A_BYTES = 128 * 128;             // 128 rows x 64 bf16
   static constexpr int B_BYTES = (BLOCK_N / CG) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (STAGE_BYTES > 40 * 1024) ? 4 : (STAGE_BYTES > 36 * 1024 ? 5 : 6);
+  static constexpr int BAR_BYTES = EPI ? 1024 : 256;
+  static constexpr int EPI_F_BYTES = 128 * 64, EPI_H_BYTES = 128 * 32;          // per half-group: fp32 / bf16 16-column slice
+  static constexpr int NBF = (EPI == 2) ? 4 : 1, NBH = (EPI == 2) ? 2 : 1;       // staging ring depth per half-group
+  static constexpr int EPI_BYTES = EPI ? 2 * (NBF * EPI_F_BYTES + NBH * EPI_H_BYTES) : 0;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - BAR_BYTES - EPI_BYTES;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int BAR_BYTES = 256;
   static constexpr int STAGE_OFF = STAGES * STAGE_BYTES + BAR_BYTES;            // epilogue staging, from smem_base
-  static constexpr int EPI_BYTES = 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_BYTES;
+  static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
 constexpr int kEpiWarps = 8;                            // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 
-template <int BLOCK_N, int CG>
+template <int BLOCK_N, int CG, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
-  using Cfg = TcCfg<BLOCK_N, CG>;
+  using Cfg = TcCfg<BLOCK_N, CG, EPI>;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs), 1 = peer
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -97,7 +134,16 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.w2);
     tma_prefetch_desc(&maps.a[0]);
+    if (EPI >= 1) {
+      tma_prefetch_desc(&maps.o);
+      tma_prefetch_desc(&maps.o2);
+    }
+    if (EPI == 2) {
+      tma_prefetch_desc(&maps.r);
+      for (int i = 0; i < 8; ++i) mbar_init(bar_base + 8u * (2 * STAGES + 6 + i), 1);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);               // CG = 2: the leader expects BOTH CTAs' TMA bytes on its barrier
       mbar_init(empty_bar(s), 1);
@@ -118,8 +164,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // tile walk: CG = 2 steps over tile PAIRS (two consecutive m-tiles); this CTA owns m_tile = 2 * pair + rank
-  const int m_units = (p.m_tiles + CG - 1) / CG;
-  const int total_tiles = m_units * p.n_tiles;
+  const int total_tiles = p.total_items;
   const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
   const int TB = 128 >> (p.tw_log2 + p.th_log2);
 
@@ -128,13 +173,15 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-      const int m_unit = tile / p.n_tiles, n_tile = tile - m_unit * p.n_tiles;
-      const int m_tile = m_unit * CG + (int)rank;       // may be == m_tiles for the odd tail: TMA zero-fills (batch coord OOB)
+      const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
+      const int m_tile = ti.m_unit * CG + (int)rank;    // may be == m_tiles for the odd tail: TMA zero-fills (batch coord OOB)
       const int xt = m_tile % p.tiles_x;
       const int r = m_tile / p.tiles_x;
       const int yt = r % p.tiles_y, bt = r / p.tiles_y;
       const int x0 = xt << p.tw_log2, y0 = yt << p.th_log2, b0 = bt * TB;
-      const int n0 = n_tile * BLOCK_N + (int)rank * (BLOCK_N / CG);   // this CTA's slice of the B rows
+      const int n0 = ti.n_tile * BLOCK_N + ti.n_off + (int)rank * (ti.w / CG);   // this CTA's slice of the B rows
+      const CUtensorMap* wm = (ti.w == BLOCK_N) ? &maps.w : &maps.w2;
+      const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + (ti.w / CG) * 128);
       for (int e = 0; e < p.ntaps; ++e) {
         const TapEntry t = p.taps[e];
         const CUtensorMap* am = &maps.a[t.map_id];
@@ -147,13 +194,13 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               // (expecting the bytes of both CTAs): a remote arrive per k-block from the peer costs ~1 us of release latency
               // and starves the MMA (measured).  The signed tx-count makes early peer completions harmless, and the peer
               // cannot run a phase ahead because its stage is only freed by the leader's multicast commit.
-              if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
               tma_load_4d_2sm(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
-              tma_load_2d_2sm(a_dst + Cfg::A_BYTES, &maps.w, full_bar(stage), t.wk0 + c * 64, n0);
+              tma_load_2d_2sm(a_dst + Cfg::A_BYTES, wm, full_bar(stage), t.wk0 + c * 64, n0);
             } else {
-              mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+              mbar_arrive_expect_tx(full_bar(stage), stage_tx);
               tma_load_4d(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
-              tma_load_2d(a_dst + Cfg::A_BYTES, &maps.w, full_bar(stage), t.wk0 + c * 64, n0);
+              tma_load_2d(a_dst + Cfg::A_BYTES, wm, full_bar(stage), t.wk0 + c * 64, n0);
             }
           }
           __syncwarp();
@@ -163,7 +210,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (CG = 2: leader CTA only)
-    constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BLOCK_N);
+    constexpr uint32_t idesc_full = umma_idesc_bf16(128 * CG, BLOCK_N);
+    constexpr uint32_t idesc_half = umma_idesc_bf16(128 * CG, BLOCK_N / 2);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -173,6 +221,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
+      const uint32_t idesc = (tile < p.full_items) ? idesc_full : idesc_half;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -197,6 +246,195 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
+  } else if (EPI >= 1) {
+    // ------------------------------------------------------------ epilogue, TMA variants (fp32 out [+ bf16 copy + LN stats])
+    // Half-group h = warps {2..5} / {6..9} owns columns [32 c + 16 h, +16) of every 32-column chunk c of the tile: per chunk
+    // each thread reads 16 accumulator columns of its row, applies bias / row bias / residual, writes the fp32 (and bf16)
+    // values into the half-group's swizzled staging slice, and the elected thread issues one TMA store per slice.  The two
+    // half-groups never synchronise with each other, so one slice drains while the other is being filled.
+    constexpr int NBF = Cfg::NBF, NBH = Cfg::NBH;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const bool elected = (warp == 2 + 4 * half) && lane == 0;
+    const int tw = row & ((1 << p.tw_log2) - 1);
+    const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+    const int tb = row >> (p.tw_log2 + p.th_log2);
+    const uint32_t st_f = smem_base + Cfg::STAGE_OFF + half * (NBF * Cfg::EPI_F_BYTES);
+    const uint32_t st_h = smem_base + Cfg::STAGE_OFF + 2 * NBF * Cfg::EPI_F_BYTES + half * (NBH * Cfg::EPI_H_BYTES);
+    const uint32_t sw64 = (uint32_t)(row >> 1) & 3u;      // SWIZZLE_64B: 16-B chunk ^= (row / 2) % 4
+    const uint32_t sw32 = (uint32_t)(row >> 2) & 1u;      // SWIZZLE_32B: 16-B chunk ^= (row / 4) % 2
+    auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + half * 4 + b); };
+    const uint32_t tempty_leader0 = (CG == 2 && rank != 0) ? mapa_shared(tempty_bar(0), 0) : 0u;
+    int it = 0;
+    uint32_t g = 0;                                       // chunks processed so far by this half-group (ring position)
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
+      const int m_tile = ti.m_unit * CG + (int)rank;
+      const int xt = m_tile % p.tiles_x;
+      const int r = m_tile / p.tiles_x;
+      const int yt = r % p.tiles_y, bt = r / p.tiles_y;
+      const int x0 = xt << p.tw_log2, y0 = yt << p.th_log2, b0 = bt * TB;
+      const int x = x0 + tw, y = y0 + th, b = b0 + tb;
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B) && (m_tile < p.m_tiles);
+      const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+      const int n_base = ti.n_tile * BLOCK_N + ti.n_off;
+      const int n0 = n_base + 16 * half;                    // first column of this half-group's slice of chunk 0
+      int nch = ti.w >> 5;                                  // 32-column chunks of this item that exist in the output
+      if ((p.N - n_base) < ti.w) nch = (p.N - n_base) >> 5;
+      const float* rb = (p.rowbias != nullptr && valid) ? p.rowbias + (pix / p.rows_per_batch) * (long long)p.N : nullptr;
+      const bool res32 = (EPI == 1) && (p.residual != nullptr) && p.res_f32 && valid;
+      const bool res16 = (p.residual != nullptr) && !p.res_f32 && valid;
+      const float* res_row = static_cast<const float*>(p.residual) + pix * p.ldr;
+      float st_sum = 0.f, st_sq = 0.f;
+
+      auto issue_res = [&](int c, uint32_t gg) {            // elected thread, EPI == 2
+        const uint32_t bb = gg & 3u;
+        mbar_arrive_expect_tx(res_full((int)bb), Cfg::EPI_F_BYTES);
+        tma_load_4d(st_f + bb * Cfg::EPI_F_BYTES, &maps.r, res_full((int)bb), n0 + c * 32, x0, y0, b0);
+      };
+      float rpre[2][16];
+      auto load_res = [&](int c, float (&dst)[16]) {
+        ldg256(res_row + n0 + c * 32, &dst[0]);
+        ldg256(res_row + n0 + c * 32 + 8, &dst[8]);
+      };
+      if (EPI == 2) {
+        if (elected) {
+          bulk_wait_read_1();                               // every slice but the one stored last is free again
+          issue_res(0, g);
+          if (nch > 1) issue_res(1, g + 1);
+        }
+      } else {
+        if (res32) {
+          load_res(0, rpre[0]);
+          if (nch > 1) load_res(1, rpre[1]);
+        }
+        // pull the NEXT item's residual rows (this half-group's slices) into L2 while this one is processed
+        if ((p.residual != nullptr) && p.res_f32 && tile + unit_step < total_tiles) {
+          const TcItem ti2 = tc_decode_item(p, tile + unit_step, BLOCK_N);
+          const int m_tile2 = ti2.m_unit * CG + (int)rank;
+          const int xt2 = m_tile2 % p.tiles_x;
+          const int r2 = m_tile2 / p.tiles_x;
+          const int yt2 = r2 % p.tiles_y, bt2 = r2 / p.tiles_y;
+          const int x2 = (xt2 << p.tw_log2) + tw, y2 = (yt2 << p.th_log2) + th, b2 = bt2 * TB + tb;
+          if ((x2 < p.Wo) && (y2 < p.Ho) && (b2 < p.B) && (m_tile2 < p.m_tiles)) {
+            const long long pix2 = ((long long)b2 * p.Ho + y2) * p.Wo + x2;
+            const int col2 = ti2.n_tile * BLOCK_N + ti2.n_off + 16 * half;
+            const float* rrow = static_cast<const float*>(p.residual) + pix2 * p.ldr + col2;
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 32; ++i)
+              if (i < (ti2.w >> 5) && col2 + i * 32 < p.N)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + i * 32));
+          }
+        }
+      }
+
+      mbar_wait(tfull_bar(buf), use & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + 16 * half);
+
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        if (c < nch) {                                          // uniform over the half-group
+          const int n = n0 + c * 32;
+          const uint32_t f_row = st_f + (NBF > 1 ? (g & 3u) * Cfg::EPI_F_BYTES : 0u) + row * 64;
+          const uint32_t h_row = st_h + (NBH > 1 ? (g & 1u) * Cfg::EPI_H_BYTES : 0u) + row * 32;
+          uint32_t v[16];
+          tmem_ld_32x16(t_row + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          if (c == nch - 1) {                                   // last TMEM read of this item: release the accumulator early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2 && rank != 0) mbar_arrive_cluster(tempty_leader0 + 8u * buf);
+              else mbar_arrive(tempty_bar(buf));
+            }
+          }
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (valid) {
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              }
+            }
+            if (rb != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              }
+            }
+            if (res32) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += rpre[c & 1][i];
+              if (c + 2 < nch) load_res(c + 2, rpre[c & 1]);
+            } else if (res16) {
+              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + n);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const uint4 rv = __ldg(rp + i);
+                float2 t;
+                t = unpack_bf16x2(rv.x); f[8 * i + 0] += t.x; f[8 * i + 1] += t.y;
+                t = unpack_bf16x2(rv.y); f[8 * i + 2] += t.x; f[8 * i + 3] += t.y;
+                t = unpack_bf16x2(rv.z); f[8 * i + 4] += t.x; f[8 * i + 5] += t.y;
+                t = unpack_bf16x2(rv.w); f[8 * i + 6] += t.x; f[8 * i + 7] += t.y;
+              }
+            }
+          }
+          // staging slices of this chunk must be free: EPI 1 -> the previous store has been read out; EPI 2 -> all but the
+          // previous one (ring), which also frees the slice that receives the residual of chunk c + 2
+          if (elected) {
+            if (EPI == 2) {
+              bulk_wait_read_1();
+              if (c + 2 < nch) issue_res(c + 2, g + 2);
+            } else {
+              bulk_wait_read_all();
+            }
+          }
+          named_bar_sync(1 + half, 128);
+          if (EPI == 2) {
+            mbar_wait(res_full((int)(g & 3u)), (g >> 2) & 1u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 rv = lds128(f_row + (((uint32_t)j ^ sw64) << 4));
+              f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
+            }
+          }
+          if (p.stats_out != nullptr && valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { st_sum += f[i]; st_sq += f[i] * f[i]; }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sts128(f_row + (((uint32_t)j ^ sw64) << 4), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          if (p.out2 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              sts128u(h_row + (((uint32_t)j ^ sw32) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                      pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + half, 128);
+          if (elected) {
+            tma_store_4d(&maps.o, f_row - row * 64, n, x0, y0, b0);
+            if (p.out2 != nullptr) tma_store_4d(&maps.o2, h_row - row * 32, n, x0, y0, b0);
+            bulk_commit_group();
+          }
+          ++g;
+        }
+      }
+      if (p.stats_out != nullptr && valid) {
+        float* sp = p.stats_out + (pix * p.n_tiles + ti.n_tile) * 8;
+        if (ti.w == BLOCK_N) *reinterpret_cast<float4*>(sp + half * 4) = make_float4(st_sum, st_sq, 0.f, 0.f);
+        else *reinterpret_cast<float2*>(sp + ((ti.n_off != 0 ? 2 : 0) + half) * 2) = make_float2(st_sum, st_sq);
+      }
+    }
+    if (elected) bulk_wait_read_all();                          // staging memory must outlive the last store's read
   } else {
     // ------------------------------------------------------------ epilogue (4 warps, one accumulator row per thread)
     // TMEM -> registers hands every thread one output row.  Shared memory is NOT used here on purpose: with
@@ -211,22 +449,24 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
     const int tb = row >> (p.tw_log2 + p.th_log2);
     constexpr int NCH = BLOCK_N / 32;
-    constexpr int NCH0 = (NCH + 1) / 2;                   // chunks [0, NCH0) -> half 0, [NCH0, NCH) -> half 1
-    const int c_lo = half == 0 ? 0 : NCH0, c_hi = half == 0 ? NCH0 : NCH;
+    constexpr int NCH0 = (NCH + 1) / 2;                   // chunks [0, NCH0) -> half 0, [NCH0, NCH) -> half 1 (full tile)
     const uint32_t tempty_leader0 = (CG == 2 && rank != 0) ? mapa_shared(tempty_bar(0), 0) : 0u;
     int it = 0;
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      const int m_unit = tile / p.n_tiles, n_tile = tile - m_unit * p.n_tiles;
-      const int m_tile = m_unit * CG + (int)rank;
+      const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
+      const int n_tile = ti.n_tile;
+      const int m_tile = ti.m_unit * CG + (int)rank;
       const int xt = m_tile % p.tiles_x;
       const int r = m_tile / p.tiles_x;
       const int yt = r % p.tiles_y, bt = r / p.tiles_y;
       const int x = (xt << p.tw_log2) + tw, y = (yt << p.th_log2) + th, b = bt * TB + tb;
       const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B) && (m_tile < p.m_tiles);
       const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
-      const int n0 = n_tile * BLOCK_N;
+      const int n0 = n_tile * BLOCK_N + ti.n_off;           // first output column of this item
+      const int nch = ti.w >> 5, nch0 = (nch + 1) >> 1;     // 32-column chunks of this item, and of its first half
+      const int c_lo = half == 0 ? 0 : nch0, c_hi = half == 0 ? nch0 : nch;
       const float* rb = (p.rowbias != nullptr && valid) ? p.rowbias + (pix / p.rows_per_batch) * (long long)p.N : nullptr;
       const bool res32 = (p.residual != nullptr) && p.res_f32 && valid && !p.geglu;
       const float* res_row = static_cast<const float*>(p.residual) + pix * p.ldr;
@@ -260,18 +500,21 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       // epilogue of residual GEMMs with short K is latency-bound on these reads otherwise
       if ((p.residual != nullptr) && p.res_f32 && !p.geglu && tile + unit_step < total_tiles) {
         const int tile2 = tile + unit_step;
-        const int m_unit2 = tile2 / p.n_tiles, n_tile2 = tile2 - m_unit2 * p.n_tiles;
-        const int m_tile2 = m_unit2 * CG + (int)rank;
+        const TcItem ti2 = tc_decode_item(p, tile2, BLOCK_N);
+        const int m_tile2 = ti2.m_unit * CG + (int)rank;
         const int xt2 = m_tile2 % p.tiles_x;
         const int r2 = m_tile2 / p.tiles_x;
         const int yt2 = r2 % p.tiles_y, bt2 = r2 / p.tiles_y;
         const int x2 = (xt2 << p.tw_log2) + tw, y2 = (yt2 << p.th_log2) + th, b2 = bt2 * TB + tb;
         if ((x2 < p.Wo) && (y2 < p.Ho) && (b2 < p.B) && (m_tile2 < p.m_tiles)) {
           const long long pix2 = ((long long)b2 * p.Ho + y2) * p.Wo + x2;
-          const float* rrow = static_cast<const float*>(p.residual) + pix2 * p.ldr + n_tile2 * BLOCK_N + c_lo * 32;
+          const int nch2 = ti2.w >> 5, nch20 = (nch2 + 1) >> 1;
+          const int c2_lo = half == 0 ? 0 : nch20, c2_n = half == 0 ? nch20 : nch2 - nch20;
+          const int col2 = ti2.n_tile * BLOCK_N + ti2.n_off + c2_lo * 32;
+          const float* rrow = static_cast<const float*>(p.residual) + pix2 * p.ldr + col2;
 #pragma unroll
-          for (int i = 0; i < (NCH0 * 32 * 4) / 128; ++i)
-            if (n_tile2 * BLOCK_N + c_lo * 32 + i * 32 < p.N)
+          for (int i = 0; i < NCH0; ++i)
+            if (i < c2_n && col2 + i * 32 < p.N)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + i * 32));
         }
       }
@@ -368,7 +611,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       } else {
         // GEGLU: W rows interleaved in 32-row groups [value | gate]; out col = n/2 + i:  value * gelu_erf(gate)
 #pragma unroll 1
-        for (int c = half; c < BLOCK_N / 64; c += 2) {           // value/gate chunk pairs alternate between the two halves
+        for (int c = half; c < (ti.w >> 6); c += 2) {            // value/gate chunk pairs alternate between the two halves
           const int n = n0 + c * 64;
           if (n >= p.N) break;                                   // warp-uniform
           uint32_t vv[32], vg[32];
@@ -410,8 +653,13 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         }
       }
-      if (p.stats_out != nullptr && valid)
-        *reinterpret_cast<float2*>(p.stats_out + ((pix * p.n_tiles + n_tile) * 2 + half) * 2) = make_float2(st_sum, st_sq);
+      // four partial-sum slots per (row, n tile): a whole tile fills {half 0, -, half 1, -} (the unused ones with zeros), a
+      // tail-split slice `sub` fills {2 sub + half}
+      if (p.stats_out != nullptr && valid) {
+        float* sp = p.stats_out + (pix * p.n_tiles + n_tile) * 8;
+        if (ti.w == BLOCK_N) *reinterpret_cast<float4*>(sp + half * 4) = make_float4(st_sum, st_sq, 0.f, 0.f);
+        else *reinterpret_cast<float2*>(sp + ((ti.n_off != 0 ? 2 : 0) + half) * 2) = make_float2(st_sum, st_sq);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -448,9 +696,12 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 tensor map, rank <= 4, dims/strides innermost-first; strides in ELEMENTS (stride of dim 0 is 1).
+// Tensor map, rank <= 4, dims/strides innermost-first; strides in ELEMENTS (stride of dim 0 is 1).  Default: bf16 operand
+// tiles with SWIZZLE_128B; the epilogue staging slices use fp32 / SWIZZLE_64B and bf16 / SWIZZLE_32B.
 static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
-                    const uint32_t* box) {
+                    const uint32_t* box, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
+  const uint64_t esz = (dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32) ? 4 : 2;
   EncodeTiledFn enc = get_encode();
   IA2P_REQUIRE(enc != nullptr, IA2P_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[4], gstr[3];
@@ -460,13 +711,13 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
     bx[i] = box[i];
     es[i] = 1;
     if (i > 0) {
-      gstr[i - 1] = strides_el[i] * 2;
+      gstr[i - 1] = strides_el[i] * esz;
       IA2P_REQUIRE(gstr[i - 1] % 16 == 0, IA2P_E_ALIGN, "tensor-map stride %llu B not a multiple of 16", (unsigned long long)gstr[i - 1]);
     }
   }
   IA2P_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IA2P_E_ALIGN, "tensor-map base not 16-byte aligned");
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IA2P_REQUIRE(r == CUDA_SUCCESS, IA2P_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
   return 0;
@@ -484,18 +735,41 @@ static int pick_block_n(int64_t N, bool geglu) {
   return 128;
 }
 
-template <int BN, int CG>
+static bool tail_split_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA2P_GEMM_TAILSPLIT");       // experiments only: 0 disables
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <int BN, int CG, int EPI>
 static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN, CG>;
+  using Cfg = TcCfg<BN, CG, EPI>;
   static bool attr_done = false;   // benign race: idempotent
   if (!attr_done) {
-    IA2P_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    IA2P_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   p.n_tiles = (p.N + BN - 1) / BN;
   const int units = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
   const int max_units = sm_count() / CG;
   const int grid = (units < max_units ? units : max_units) * CG;
+  // Tail split: with r = units mod G tiles left for a last wave that would occupy r of G CTAs (pairs), cut those tiles into
+  // two column halves when both halves still fit in ONE wave (a half tile costs ~0.6 of a whole one: the main loop of a
+  // narrower tile is bound by the A-operand traffic).  Needs BLOCK_N / 2 to be a whole number of 32-column epilogue chunks
+  // (64-column value|gate groups for GEGLU) and N a multiple of BLOCK_N (no ragged last tile).
+  p.full_items = units;
+  p.total_items = units;
+  p.split = 1;
+  const int rem = units % max_units;
+  const bool can_split = tail_split_enabled() && (BN % 64 == 0) && (!p.geglu || BN % 128 == 0) && (p.N % BN == 0);
+  if (can_split && units > max_units && rem != 0 && 2 * rem <= max_units) {
+    p.split = 2;
+    p.full_items = units - rem;
+    p.total_items = p.full_items + 2 * rem;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kTcThreads);
@@ -508,7 +782,7 @@ static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IA2P_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG>, maps, p));
+  IA2P_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG, EPI>, maps, p));
   IA2P_LAUNCH_CHECK();
   return 0;
 }
@@ -526,12 +800,61 @@ static int gemm_cg_override() {
   return v;
 }
 
-static int dispatch_tc(const TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
+// fp32 outputs go through the TMA-store epilogue (EPI = 1); IA2P_GEMM_EPI=0 forces the register-store epilogue (experiments)
+static bool tma_epilogue(const TcParams& p) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA2P_GEMM_EPI");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0 && p.out_f32 && !p.geglu;
+}
+
+// EPI = 2 (TMA-loaded residual, one main-loop stage fewer) pays when the main loop of a tile is short: K <= 1536
+static bool tma_residual(const TcParams& p) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA2P_GEMM_EPI");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0 && tma_epilogue(p) && p.residual != nullptr && p.res_f32 && p.num_kb <= 24;
+}
+
+template <int BN>
+static int dispatch_bn(const TcMaps& maps, TcParams& p, cudaStream_t st) {
   const bool pair = gemm_cg_override() == 2 && p.m_tiles >= 2;
+  if (tma_residual(p)) return pair ? launch_tc<BN, 2, 2>(maps, p, st) : launch_tc<BN, 1, 2>(maps, p, st);
+  if (tma_epilogue(p)) return pair ? launch_tc<BN, 2, 1>(maps, p, st) : launch_tc<BN, 1, 1>(maps, p, st);
+  return pair ? launch_tc<BN, 2, 0>(maps, p, st) : launch_tc<BN, 1, 0>(maps, p, st);
+}
+
+static int dispatch_tc(TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
+  if (tma_epilogue(p)) {
+    // output maps: same pixel-box geometry as the A operand, 16 columns wide
+    const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TB = 128 >> (p.tw_log2 + p.th_log2);
+    const uint32_t box[4] = {16, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+    const uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
+    const uint64_t str[4] = {1, (uint64_t)p.ldo, (uint64_t)p.ldo * p.Wo, (uint64_t)p.ldo * p.Wo * p.Ho};
+    if (int e = make_map(&maps.o, p.out, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    maps.o2 = maps.o;
+    if (p.out2 != nullptr) {
+      const uint64_t str2[4] = {1, (uint64_t)p.ldo2, (uint64_t)p.ldo2 * p.Wo, (uint64_t)p.ldo2 * p.Wo * p.Ho};
+      if (int e = make_map(&maps.o2, p.out2, 4, dims, str2, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
+    }
+    maps.r = maps.o;
+    if (tma_residual(p)) {
+      const uint64_t strr[4] = {1, (uint64_t)p.ldr, (uint64_t)p.ldr * p.Wo, (uint64_t)p.ldr * p.Wo * p.Ho};
+      if (int e = make_map(&maps.r, p.residual, 4, dims, strr, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    }
+  } else {
+    maps.o = maps.w;                 // unused: keep the kernel parameter defined
+    maps.o2 = maps.w;
+    maps.r = maps.w;
+  }
   switch (bn) {
-    case 256: return pair ? launch_tc<256, 2>(maps, p, st) : launch_tc<256, 1>(maps, p, st);
-    case 160: return pair ? launch_tc<160, 2>(maps, p, st) : launch_tc<160, 1>(maps, p, st);
-    default: return pair ? launch_tc<128, 2>(maps, p, st) : launch_tc<128, 1>(maps, p, st);
+    case 256: return dispatch_bn<256>(maps, p, st);
+    case 160: return dispatch_bn<160>(maps, p, st);
+    default: return dispatch_bn<128>(maps, p, st);
   }
 }
 
@@ -540,7 +863,9 @@ static int make_w_map(TcMaps& maps, const void* W, int64_t N, int64_t Ktot, int 
   const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
   const uint64_t str[2] = {1, (uint64_t)Ktot};
   const uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
-  return make_map(&maps.w, W, 2, dims, str, box);
+  if (int e = make_map(&maps.w, W, 2, dims, str, box)) return e;
+  const uint32_t box2[2] = {64, (uint32_t)((bn % 64 == 0) ? box[1] / 2 : box[1])};   // half tiles (tail split)
+  return make_map(&maps.w2, W, 2, dims, str, box2);
 }
 
 static int ilog2_exact(int v) {
@@ -561,7 +886,7 @@ extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void
                            out_dtype, epilogue, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, stream);
 }
 
-extern "C" int64_t ia2p_gemm_ln_parts(int64_t N) { return 2 * ((N + pick_block_n(N, false) - 1) / pick_block_n(N, false)); }
+extern "C" int64_t ia2p_gemm_ln_parts(int64_t N) { return 4 * ((N + pick_block_n(N, false) - 1) / pick_block_n(N, false)); }
 
 extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                                  const void* W, void* out, int64_t ldo, int64_t M, int64_t N,

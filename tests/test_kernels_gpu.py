@@ -38,6 +38,27 @@ def test_gemm_plain(M, N, K):
     assert rel(out, a.float() @ w.float().t()) < TOL
 
 
+@pytest.mark.parametrize("mode", ["plain", "res32_ln", "geglu"])
+def test_gemm_tail_split(mode):
+    """tile counts that leave a small last wave (here 160 and 320 tiles on 148 SMs) run that wave as half-width tiles."""
+    from instructany2pix_b200.packing import interleave_geglu
+    M, N, K = (2048, 2560, 192) if mode != "geglu" else (2048 * 2, 2560, 128)
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    ref = a.float() @ w.float().t()
+    if mode == "plain":
+        assert rel(ops.gemm(a, w), ref) < TOL
+    elif mode == "res32_ln":
+        res = rnd(M, N, dtype=torch.float32)
+        t, tb, st = ops.gemm(a, w, residual=res, out_dtype=torch.float32, want_ln=True)
+        assert rel(t, ref + res) < 2e-6 and torch.equal(tb, t.to(torch.bfloat16))
+        assert rel(st.sum(1)[:, 0], t.sum(1)) < 1e-5 and rel(st.sum(1)[:, 1], (t * t).sum(1)) < 1e-5
+    else:
+        b = rnd(N, dtype=torch.float32, scale=0.1)
+        wi, bi = interleave_geglu(w, b)
+        h = ref + b
+        assert rel(ops.gemm(a, wi, bias=bi, geglu=True), h[:, :N // 2] * F.gelu(h[:, N // 2:])) < TOL
+
+
 def test_gemm_epilogues():
     M, N, K = 768, 640, 320
     a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)

@@ -49,6 +49,38 @@ def bench_gemm():
         print(f"gemm {name:14s} M={M:6d} N={N:6d} K={K:5d} {mode:6s}: {ms * 1e3:8.1f} us  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s")
 
 
+def bench_mainloop():
+    """main-loop rate in isolation: exactly one or two tiles per CTA, K so long that the epilogue is negligible"""
+    for name, M, N, K in [("1 tile/CTA", 128 * 148, 256, 16384), ("2 tiles/CTA", 128 * 148, 512, 8192), ("square 8192", 8192, 8192, 8192)]:
+        a = torch.randn(M, K, device=dev).to(BF)
+        w = (torch.randn(N, K, device=dev) * K ** -0.5).to(BF)
+        ms = timeit(lambda i: ops.gemm(a, w), iters=10)
+        print(f"mainloop {name:12s} M={M:6d} N={N:6d} K={K:5d}: {ms * 1e3:8.1f} us  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s")
+    a = torch.randn(8192, 8192, device=dev).to(BF)
+    w = torch.randn(8192, 8192, device=dev).to(BF)
+    ms = timeit(lambda i: torch.matmul(a, w.t()), iters=10)
+    print(f"cuBLAS square 8192: {ms * 1e3:8.1f} us  {2.0 * 8192 ** 3 / ms / 1e9:7.1f} TFLOP/s")
+
+
+def bench_lnfold():
+    """consumer GEMMs with and without the LayerNorm fold, producer GEMM with and without the LN outputs."""
+    M, C = 8192, 1280
+    a = [torch.randn(M, C, device=dev).to(BF) for _ in range(6)]
+    st = torch.rand(M, 10, 2, device=dev) + 1.0
+    for name, N, geglu in [("geglu", 10240, True), ("qkv", 3840, False), ("to_q", 1280, False)]:
+        w = [(torch.randn(N, C, device=dev) * C ** -0.5).to(BF) for _ in range(6)]
+        bias, c1 = torch.randn(N, device=dev), torch.randn(N, device=dev)
+        t0 = timeit(lambda i: ops.gemm(a[i % 6], w[i % 6], bias=bias, geglu=geglu))
+        t1 = timeit(lambda i: ops.gemm(a[i % 6], w[i % 6], bias=bias, geglu=geglu, ln=(st, c1, 1e-5)))
+        print(f"consumer {name:6s}: plain {t0 * 1e3:7.1f} us   ln-fold {t1 * 1e3:7.1f} us")
+    w = [(torch.randn(C, C, device=dev) * C ** -0.5).to(BF) for _ in range(6)]
+    res = [torch.randn(M, C, device=dev) for _ in range(6)]
+    bias = torch.randn(C, device=dev)
+    t0 = timeit(lambda i: ops.gemm(a[i % 6], w[i % 6], bias=bias, residual=res[i % 6], out_dtype=torch.float32))
+    t1 = timeit(lambda i: ops.gemm(a[i % 6], w[i % 6], bias=bias, residual=res[i % 6], out_dtype=torch.float32, want_ln=True))
+    print(f"producer out_proj: plain {t0 * 1e3:7.1f} us   +bf16 copy +stats {t1 * 1e3:7.1f} us")
+
+
 def bench_conv():
     for name, B, H, Cin, Cout in [("1280@32", 8, 32, 1280, 1280), ("640@64", 8, 64, 640, 640), ("320@128", 8, 128, 320, 320),
                                   ("2560->1280@32", 8, 32, 2560, 1280), ("960->320@128", 8, 128, 960, 320)]:
@@ -88,6 +120,6 @@ def bench_norm():
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.manual_seed(0)
-    for k, fn in (("gemm", bench_gemm), ("conv", bench_conv), ("attn", bench_attn), ("norm", bench_norm)):
+    for k, fn in (("gemm", bench_gemm), ("conv", bench_conv), ("attn", bench_attn), ("norm", bench_norm), ("lnfold", bench_lnfold), ("mainloop", bench_mainloop)):
         if which in (k, "all"):
             fn()
