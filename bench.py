@@ -47,6 +47,17 @@ def peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) per tc_gemm_kernel launch, averaged over the launches of one UNet forward, from the committed
+    `ncu --set full` capture (profiles/gemm_traffic_r01.json; not measured live -- a run under ncu is never a bench value)."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(dram_bytes_per_launch=d["dram_bytes_per_launch"], algorithmic_bytes_per_launch=d.get("algorithmic_bytes_per_launch"),
+                    launches=d["launches"], source="profiles/gemm_traffic_r01.json")
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -333,14 +344,14 @@ def main():
     n_forward_kernels = sum(d["n"] + (d["n"] if k == "ia2p_groupnorm_nhwc" else 0) for k, d in by.items())
     gpu_launches = launches_eager + (0 if args.no_graph else args.steps * NS * n_forward_kernels)
     tc = dict(ms=0.0, flops=0.0, n=0)
-    for k in ("ia2p_gemm_bf16", "ia2p_conv3x3_nhwc_bf16"):
+    for k in ("ia2p_gemm_bf16", "ia2p_gemm_ln_bf16", "ia2p_conv3x3_nhwc_bf16"):
         if k in by:
             for f in tc:
                 tc[f] += by[k][f]
     total_ms = sum(d["ms"] for d in by.values())
     ach = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] else 0.0
     roof = dict(kernel="tc_gemm_kernel (tcgen05 implicit GEMM: linears + 3x3 convs)", bound="tensor", achieved=ach,
-                peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"], traffic=None, peak_source=pk["src"] + " bf16_tflops_sustained",
+                peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"], traffic=ncu_traffic(), peak_source=pk["src"] + " bf16_tflops_sustained",
                 launches_per_forward=tc["n"], avg_launch_ms=tc["ms"] / max(tc["n"], 1), share_of_forward=tc["ms"] / total_ms if total_ms else None,
                 forward_breakdown_ms={k: round(d["ms"], 3) for k, d in sorted(by.items(), key=lambda kv: -kv[1]["ms"])})
     out = dict(metric="images/sec 1024^2 50-step DDIM CFG" if L == 128 else "images/sec 512^2 50-step DDIM CFG",

@@ -1,6 +1,7 @@
 // C-ABI plumbing: thread-local error string, device gate (sm_100 only; there is no CPU or other-arch fallback).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -40,6 +41,15 @@ int check_device() {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) { set_error("cudaGetDevice: %s (no CUDA device: this library has no CPU path)", cudaGetErrorString(e)); return IA2P_E_DEVICE; }
   return query_device(dev);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA2P_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
 }
 
 int sm_count() {

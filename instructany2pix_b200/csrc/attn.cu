@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(256)
 flash_self_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                        const __nv_bfloat16* __restrict__ v, long long ld, __nv_bfloat16* __restrict__ out, long long ldo,
                        int n_tokens, float scale_log2) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);            // 128 x 64
   const uint32_t sK = sQ + 128 * 128;            // 2 x (64 x 64)
@@ -182,6 +184,8 @@ cross_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv
                   const __nv_bfloat16* __restrict__ vt, long long ldkv, int n_text, const __nv_bfloat16* __restrict__ ki,
                   const __nv_bfloat16* __restrict__ vi, long long ldkv_ip, int n_ip, float ip_scale,
                   __nv_bfloat16* __restrict__ out, long long ldo, int n_q, float scale_log2) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   constexpr int TK = T1 + T2;
   constexpr int NT = TK / 8, NT1 = T1 / 8;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -337,7 +341,7 @@ static int launch_cross(const void* q, int64_t ldq, const void* kt, const void* 
   for (int d = 1; d <= n_qtiles; ++d)
     if (n_qtiles % d == 0 && (long long)d * heads * batch >= 3LL * sm_count()) { split = d; break; }
   const dim3 grid((unsigned)split, (unsigned)heads, (unsigned)batch);
-  cross_attn_kernel<T1, T2><<<grid, 256, smem, st>>>(
+  launch_pdl(cross_attn_kernel<T1, T2>, dim3(grid), dim3(256), smem, st, 
       static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(kt), static_cast<const __nv_bfloat16*>(vt),
       ldkv, n_text, static_cast<const __nv_bfloat16*>(ki), static_cast<const __nv_bfloat16*>(vi), ldkv_ip, n_ip, ip_scale,
       static_cast<__nv_bfloat16*>(out), ldo, (int)n_q, scale * kLog2e);

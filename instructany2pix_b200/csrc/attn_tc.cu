@@ -28,6 +28,7 @@ constexpr float kRescaleThreshold = 8.0f;
 
 __global__ void __launch_bounds__(192, 2)
 fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ out, long long ldo, int n_tokens, float scale_log2) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 128u + 1023u) & ~1023u;       // >= 128 B of barriers in front
@@ -57,6 +58,7 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  pdl_wait();                // barrier init / TMEM allocation above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -295,7 +297,7 @@ int launch_fa_tc(const void* q, const void* k, const void* v, int64_t ld, void* 
     done = true;
   }
   const dim3 grid((unsigned)((n_tokens + 127) / 128), (unsigned)heads, (unsigned)batch);
-  fa_tc_kernel<<<grid, 192, kFaSmemBytes, st>>>(maps, static_cast<__nv_bfloat16*>(out), ldo, (int)n_tokens,
+  launch_pdl(fa_tc_kernel, dim3(grid), dim3(192), kFaSmemBytes, st, maps, static_cast<__nv_bfloat16*>(out), ldo, (int)n_tokens,
                                                 softmax_scale * 1.4426950408889634f);
   IA2P_LAUNCH_CHECK();
   return 0;

@@ -8,6 +8,8 @@ namespace ia2p {
 template <typename TE, typename TX, typename TI>
 __global__ void cfg_ddim_kernel(const TE* __restrict__ eps2, const TX* __restrict__ x, TX* __restrict__ x_out,
                                 TI* __restrict__ x_in2, long long total, float g, float cx, float ce) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   // total = batch * n; eps_u at [i], eps_c at [total + i]
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total;
        i += (long long)gridDim.x * blockDim.x * 4) {
@@ -28,6 +30,8 @@ __global__ void cfg_ddim_kernel(const TE* __restrict__ eps2, const TX* __restric
 template <typename TE, typename TX>
 __global__ void axpby_kernel(const TE* __restrict__ eps, const TX* __restrict__ x, TX* __restrict__ out, long long n,
                              float cx, float ce) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     store_from_float(out + i, cx * load_as_float(x + i) + ce * load_as_float(eps + i));
 }
@@ -35,6 +39,8 @@ __global__ void axpby_kernel(const TE* __restrict__ eps, const TX* __restrict__ 
 __global__ void prior_step_kernel(const float* __restrict__ x0_pair, const float* __restrict__ x,
                                   const float* __restrict__ noise, float* __restrict__ out, long long n, float sqrt_a,
                                   float sqrt_1ma, float g, float c_x0, float c_x, float sigma) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float xv = x[i];
     const float ec = (xv - sqrt_a * x0_pair[i]) / sqrt_1ma;        // get_eps, cond half first
@@ -50,6 +56,8 @@ __global__ void prior_step_kernel(const float* __restrict__ x0_pair, const float
 template <typename TO>
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, long long n, int dim, int flip, float shift,
                                           TO* __restrict__ out) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int half = dim / 2;
   const long long total = n * (long long)dim;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -84,6 +92,8 @@ __device__ __forceinline__ uint4 load8_as_bf16(const __half* p) {
 
 template <typename T>
 __global__ void upsample2x_kernel(const T* __restrict__ x, uint4* __restrict__ y, long long batch, int h, int w, int cv) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   // cv = C/8 vectors per pixel; output pixel (oy, ox) <- input (oy>>1, ox>>1); output bf16 (conv operand)
   const long long total = batch * (long long)(2 * h) * (2 * w) * cv;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -100,6 +110,8 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, uint4* __restrict__ y
 
 template <typename T>
 __global__ void cast_bf16_kernel(const T* __restrict__ x, uint4* __restrict__ y, long long nvec) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x)
     y[i] = load8_as_bf16(x + i * 8);
 }
@@ -113,6 +125,8 @@ template <typename TX, typename TO>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const TX* __restrict__ x, long long in_batch, long long B, int H, int W, int Cin,
                const float* __restrict__ w, const float* __restrict__ bias, TO* __restrict__ out, int Cout) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   extern __shared__ float sm[];
   const int K = Cin * 9;
   float* sw = sm;                       // [K][Cout]
@@ -160,6 +174,8 @@ conv_in_kernel(const TX* __restrict__ x, long long in_batch, long long B, int H,
 template <typename TO, int COUT>
 __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, long long B, int H, int W, int Cin,
                                 const float* __restrict__ w, const float* __restrict__ bias, TO* __restrict__ out) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -232,7 +248,7 @@ extern "C" int ia2p_cfg_ddim_step(const void* eps2, int eps_dtype, const void* x
   const int grid = grid_for(total / 4, 256);
   if (x_in_next2 == nullptr) xin_dtype = x_dtype;
   DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(xin_dtype, TI,
-      (cfg_ddim_kernel<TE, TX, TI><<<grid, 256, 0, st>>>(static_cast<const TE*>(eps2), static_cast<const TX*>(x),
+      (launch_pdl(cfg_ddim_kernel<TE, TX, TI>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps2), static_cast<const TX*>(x),
                                                          static_cast<TX*>(x_out), static_cast<TI*>(x_in_next2), total,
                                                          g, c_x, c_e)))));
   IA2P_LAUNCH_CHECK();
@@ -246,7 +262,7 @@ extern "C" int ia2p_axpby(const void* eps, int eps_dtype, const void* x, void* x
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(n, 256);
   DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX,
-      (axpby_kernel<TE, TX><<<grid, 256, 0, st>>>(static_cast<const TE*>(eps), static_cast<const TX*>(x),
+      (launch_pdl(axpby_kernel<TE, TX>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps), static_cast<const TX*>(x),
                                                   static_cast<TX*>(x_out), n, c_x, c_e))));
   IA2P_LAUNCH_CHECK();
   return 0;
@@ -270,7 +286,7 @@ extern "C" int ia2p_timestep_embedding(const float* t, int64_t n, int dim, int f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(n * dim, 256);
   DISPATCH_DTYPE(out_dtype, TO,
-      (timestep_embedding_kernel<TO><<<grid, 256, 0, st>>>(t, n, dim, flip_sin_to_cos, shift, static_cast<TO*>(out))));
+      (launch_pdl(timestep_embedding_kernel<TO>, dim3(grid), dim3(256), 0, st, t, n, dim, flip_sin_to_cos, shift, static_cast<TO*>(out))));
   IA2P_LAUNCH_CHECK();
   return 0;
 }
@@ -282,7 +298,7 @@ extern "C" int ia2p_upsample2x_nhwc(const void* x, int x_dtype, void* y, int64_t
   const long long total = batch * 4 * h * w * (c / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(total, 256);
-  DISPATCH_DTYPE(x_dtype, TX, (upsample2x_kernel<TX><<<grid, 256, 0, st>>>(static_cast<const TX*>(x), static_cast<uint4*>(y),
+  DISPATCH_DTYPE(x_dtype, TX, (launch_pdl(upsample2x_kernel<TX>, dim3(grid), dim3(256), 0, st, static_cast<const TX*>(x), static_cast<uint4*>(y),
                                                                           batch, (int)h, (int)w, (int)(c / 8))));
   IA2P_LAUNCH_CHECK();
   return 0;
@@ -294,7 +310,7 @@ extern "C" int ia2p_cast_to_bf16(const void* x, int x_dtype, void* y, int64_t n,
   IA2P_REQUIRE(n % 8 == 0, IA2P_E_SHAPE, "cast_to_bf16: n=%lld must be a multiple of 8", (long long)n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(n / 8, 256);
-  DISPATCH_DTYPE(x_dtype, TX, (cast_bf16_kernel<TX><<<grid, 256, 0, st>>>(static_cast<const TX*>(x), static_cast<uint4*>(y), n / 8)));
+  DISPATCH_DTYPE(x_dtype, TX, (launch_pdl(cast_bf16_kernel<TX>, dim3(grid), dim3(256), 0, st, static_cast<const TX*>(x), static_cast<uint4*>(y), n / 8)));
   IA2P_LAUNCH_CHECK();
   return 0;
 }
@@ -314,7 +330,7 @@ extern "C" int ia2p_conv_in_nchw(const void* x, int x_dtype, int64_t in_batch, i
   do {                                                                                                                   \
     if (smem > 48 * 1024)                                                                                                \
       IA2P_CUDA(cudaFuncSetAttribute(conv_in_kernel<TX_, TO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_in_kernel<TX_, TO_><<<grid, 256, smem, st>>>(static_cast<const TX_*>(x), in_batch, B, (int)H, (int)W, (int)Cin, w, \
+    launch_pdl(conv_in_kernel<TX_, TO_>, dim3(grid), dim3(256), smem, st, static_cast<const TX_*>(x), in_batch, B, (int)H, (int)W, (int)Cin, w, \
                                                       bias, static_cast<TO_*>(out), (int)Cout);                         \
   } while (0)
   if (out_dtype == IA2P_BF16) {
@@ -335,7 +351,7 @@ extern "C" int ia2p_conv_out_nhwc(const void* x, int64_t B, int64_t H, int64_t W
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(B * H * W * 32, 256);
   DISPATCH_DTYPE(out_dtype, TO,
-      (conv_out_kernel<TO, 4><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), B, (int)H, (int)W, (int)Cin, w,
+      (launch_pdl(conv_out_kernel<TO, 4>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), B, (int)H, (int)W, (int)Cin, w,
                                                     bias, static_cast<TO*>(out))));
   IA2P_LAUNCH_CHECK();
   return 0;

@@ -41,6 +41,7 @@ struct TcParams {
   // Tail split (wave quantisation): work items [0, full_items) are whole 128 x BLOCK_N tiles; the remaining tiles -- the
   // ones that would form a last, mostly idle wave -- are cut into `split` column slices each, so that every SM gets a slice.
   int full_items, total_items, split;
+  int trace_id;                    // debug build: launch id for the in-graph timeline
   int Wo, Ho, B;                   // output pixel grid (plain GEMM: Wo = M, Ho = B = 1)
   int N;                           // GEMM N (pre-GEGLU)
   int rows_per_batch;              // rowbias row = pixel / rows_per_batch
@@ -61,6 +62,27 @@ struct TcParams {
   int ln_parts;
   float ln_inv_n, ln_eps;          // 1 / (normalised width), epsilon
 };
+
+#ifdef IA2P_TC_TRACE
+// Debug build only (tools/trace_gemm.py): per-CTA wait/busy cycle counters of the three warp roles.
+__device__ unsigned long long* g_tc_trace = nullptr;
+__device__ unsigned long long* g_tc_timeline = nullptr;        // [launch id][2] = {min start, max end} (globaltimer ns)
+static int g_tc_launch_id = 0;                                 // host: id handed to the next launch (fixed per graph node)
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE_DECL(name) long long name = 0
+#define TRACE_T0(v) const long long v = clock64()
+#define TRACE_ADD(acc, v) acc += clock64() - v
+#define TRACE_PUT(slot, val) do { if (g_tc_trace != nullptr && lane == 0) g_tc_trace[(size_t)blockIdx.x * 16 + (slot)] = (unsigned long long)(val); } while (0)
+#else
+#define TRACE_DECL(name)
+#define TRACE_T0(v)
+#define TRACE_ADD(acc, v)
+#define TRACE_PUT(slot, val)
+#endif
 
 struct TcItem { int m_unit, n_tile, n_off, w; };
 __device__ __forceinline__ TcItem tc_decode_item(const TcParams& p, int item, int block_n) {
@@ -131,6 +153,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+#ifdef IA2P_TC_TRACE
+  if (warp == 0) TRACE_PUT(0, gtime_ns());
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.w);
@@ -162,6 +188,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (CG == 2) cluster_sync_all(); else __syncthreads();        // peer barriers must be initialised before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                                                   // everything above overlapped the previous kernel's tail
+#ifdef IA2P_TC_TRACE
+  if (warp == 0) TRACE_PUT(1, gtime_ns());
+  if (threadIdx.x == 0 && g_tc_timeline != nullptr) atomicMin(g_tc_timeline + 2 * (size_t)p.trace_id, gtime_ns());
+#endif
 
   // tile walk: CG = 2 steps over tile PAIRS (two consecutive m-tiles); this CTA owns m_tile = 2 * pair + rank
   const int total_tiles = p.total_items;
@@ -172,6 +203,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    TRACE_DECL(tr_wait_empty);
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
       const int m_tile = ti.m_unit * CG + (int)rank;    // may be == m_tiles for the odd tail: TMA zero-fills (batch coord OOB)
@@ -186,7 +218,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const TapEntry t = p.taps[e];
         const CUtensorMap* am = &maps.a[t.map_id];
         for (int c = 0; c < t.nchunks; ++c) {
+          TRACE_T0(tw0);
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          TRACE_ADD(tr_wait_empty, tw0);
           if (lane == 0) {
             const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
             if (CG == 2) {
@@ -208,6 +242,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       }
     }
+    TRACE_PUT(5, tr_wait_empty);
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (CG = 2: leader CTA only)
     constexpr uint32_t idesc_full = umma_idesc_bf16(128 * CG, BLOCK_N);
@@ -215,15 +250,23 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    TRACE_DECL(tr_wait_full);
+    TRACE_DECL(tr_wait_tempty);
+    TRACE_DECL(tr_loop);
+    TRACE_T0(tl0);
     for (int tile = unit0; tile < total_tiles && rank == 0; tile += unit_step, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
+      TRACE_T0(te0);
       mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+      TRACE_ADD(tr_wait_tempty, te0);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
       const uint32_t idesc = (tile < p.full_items) ? idesc_full : idesc_half;
       for (int kb = 0; kb < p.num_kb; ++kb) {
+        TRACE_T0(tf0);
         mbar_wait(full_bar(stage), phase);
+        TRACE_ADD(tr_wait_full, tf0);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
@@ -246,6 +289,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
+    TRACE_ADD(tr_loop, tl0);
+    TRACE_PUT(2, tr_wait_full);
+    TRACE_PUT(3, tr_wait_tempty);
+    TRACE_PUT(4, tr_loop);
+    TRACE_PUT(9, it);
   } else if (EPI >= 1) {
     // ------------------------------------------------------------ epilogue, TMA variants (fp32 out [+ bf16 copy + LN stats])
     // Half-group h = warps {2..5} / {6..9} owns columns [32 c + 16 h, +16) of every 32-column chunk c of the tile: per chunk
@@ -267,6 +315,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + half * 4 + b); };
     const uint32_t tempty_leader0 = (CG == 2 && rank != 0) ? mapa_shared(tempty_bar(0), 0) : 0u;
     int it = 0;
+    TRACE_DECL(tr_wait_tfull);
+    TRACE_DECL(tr_busy);
     uint32_t g = 0;                                       // chunks processed so far by this half-group (ring position)
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
       const int buf = it & 1;
@@ -331,7 +381,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       }
 
+      TRACE_T0(tq0);
       mbar_wait(tfull_bar(buf), use & 1u);
+      TRACE_ADD(tr_wait_tfull, tq0);
+      TRACE_T0(tb0);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + 16 * half);
 
@@ -433,8 +486,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (ti.w == BLOCK_N) *reinterpret_cast<float4*>(sp + half * 4) = make_float4(st_sum, st_sq, 0.f, 0.f);
         else *reinterpret_cast<float2*>(sp + ((ti.n_off != 0 ? 2 : 0) + half) * 2) = make_float2(st_sum, st_sq);
       }
+      TRACE_ADD(tr_busy, tb0);
     }
     if (elected) bulk_wait_read_all();                          // staging memory must outlive the last store's read
+    if (warp == 2) { TRACE_PUT(6, tr_wait_tfull); TRACE_PUT(7, tr_busy); }
   } else {
     // ------------------------------------------------------------ epilogue (4 warps, one accumulator row per thread)
     // TMEM -> registers hands every thread one output row.  Shared memory is NOT used here on purpose: with
@@ -452,6 +507,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     constexpr int NCH0 = (NCH + 1) / 2;                   // chunks [0, NCH0) -> half 0, [NCH0, NCH) -> half 1 (full tile)
     const uint32_t tempty_leader0 = (CG == 2 && rank != 0) ? mapa_shared(tempty_bar(0), 0) : 0u;
     int it = 0;
+    TRACE_DECL(tr_wait_tfull);
+    TRACE_DECL(tr_busy);
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -519,7 +576,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       }
 
+      TRACE_T0(tq0);
       mbar_wait(tfull_bar(buf), use & 1u);
+      TRACE_ADD(tr_wait_tfull, tq0);
+      TRACE_T0(tb0);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N);
 
@@ -536,15 +596,17 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               float f[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-              if (p.ln_stats != nullptr) {
+              if (p.ln_stats != nullptr) {      // rstd * (acc - mean * c1) + bias = acc * rstd + (c1 * (-mean * rstd) + bias)
+                const float ln_nm = -ln_mean * ln_rstd;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                   const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + i));
-                  f[i] = ln_rstd * (f[i] - ln_mean * cv.x); f[i + 1] = ln_rstd * (f[i + 1] - ln_mean * cv.y);
-                  f[i + 2] = ln_rstd * (f[i + 2] - ln_mean * cv.z); f[i + 3] = ln_rstd * (f[i + 3] - ln_mean * cv.w);
+                  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                  f[i] = fmaf(f[i], ln_rstd, fmaf(cv.x, ln_nm, bv.x)); f[i + 1] = fmaf(f[i + 1], ln_rstd, fmaf(cv.y, ln_nm, bv.y));
+                  f[i + 2] = fmaf(f[i + 2], ln_rstd, fmaf(cv.z, ln_nm, bv.z)); f[i + 3] = fmaf(f[i + 3], ln_rstd, fmaf(cv.w, ln_nm, bv.w));
                 }
-              }
-              if (p.bias != nullptr) {
+              } else if (p.bias != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                   const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
@@ -620,6 +682,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           tmem_ld_wait();
           if (valid) {
             float f[32];
+            // LN fold as two FMAs per element: rstd * (acc - mean * c1) + bias = acc * rstd + (c1 * (-mean * rstd) + bias)
+            const float ln_nm = -ln_mean * ln_rstd;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
@@ -627,20 +691,18 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
                 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32 + i));
               }
-              float a0 = __uint_as_float(vv[i + 0]), a1 = __uint_as_float(vv[i + 1]), a2 = __uint_as_float(vv[i + 2]), a3 = __uint_as_float(vv[i + 3]);
-              float g0 = __uint_as_float(vg[i + 0]), g1 = __uint_as_float(vg[i + 1]), g2 = __uint_as_float(vg[i + 2]), g3 = __uint_as_float(vg[i + 3]);
               if (p.ln_stats != nullptr) {
                 const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + i));
                 const float4 cg = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + 32 + i));
-                a0 = ln_rstd * (a0 - ln_mean * cv.x); a1 = ln_rstd * (a1 - ln_mean * cv.y);
-                a2 = ln_rstd * (a2 - ln_mean * cv.z); a3 = ln_rstd * (a3 - ln_mean * cv.w);
-                g0 = ln_rstd * (g0 - ln_mean * cg.x); g1 = ln_rstd * (g1 - ln_mean * cg.y);
-                g2 = ln_rstd * (g2 - ln_mean * cg.z); g3 = ln_rstd * (g3 - ln_mean * cg.w);
+                bv.x = fmaf(cv.x, ln_nm, bv.x); bv.y = fmaf(cv.y, ln_nm, bv.y); bv.z = fmaf(cv.z, ln_nm, bv.z); bv.w = fmaf(cv.w, ln_nm, bv.w);
+                bg.x = fmaf(cg.x, ln_nm, bg.x); bg.y = fmaf(cg.y, ln_nm, bg.y); bg.z = fmaf(cg.z, ln_nm, bg.z); bg.w = fmaf(cg.w, ln_nm, bg.w);
               }
-              f[i + 0] = (a0 + bv.x) * gelu_erf_f(g0 + bg.x);
-              f[i + 1] = (a1 + bv.y) * gelu_erf_f(g1 + bg.y);
-              f[i + 2] = (a2 + bv.z) * gelu_erf_f(g2 + bg.z);
-              f[i + 3] = (a3 + bv.w) * gelu_erf_f(g3 + bg.w);
+              const float a0 = __uint_as_float(vv[i + 0]), a1 = __uint_as_float(vv[i + 1]), a2 = __uint_as_float(vv[i + 2]), a3 = __uint_as_float(vv[i + 3]);
+              const float g0 = __uint_as_float(vg[i + 0]), g1 = __uint_as_float(vg[i + 1]), g2 = __uint_as_float(vg[i + 2]), g3 = __uint_as_float(vg[i + 3]);
+              f[i + 0] = fmaf(a0, ln_rstd, bv.x) * gelu_erf_f(fmaf(g0, ln_rstd, bg.x));
+              f[i + 1] = fmaf(a1, ln_rstd, bv.y) * gelu_erf_f(fmaf(g1, ln_rstd, bg.y));
+              f[i + 2] = fmaf(a2, ln_rstd, bv.z) * gelu_erf_f(fmaf(g2, ln_rstd, bg.z));
+              f[i + 3] = fmaf(a3, ln_rstd, bv.w) * gelu_erf_f(fmaf(g3, ln_rstd, bg.w));
             }
             __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + (n >> 1);
 #pragma unroll
@@ -666,16 +728,24 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (CG == 2 && rank != 0) mbar_arrive_cluster(tempty_leader0 + 8u * buf);   // release the LEADER's MMA warp
         else mbar_arrive(tempty_bar(buf));
       }
+      TRACE_ADD(tr_busy, tb0);
     }
+    if (warp == 2) { TRACE_PUT(6, tr_wait_tfull); TRACE_PUT(7, tr_busy); }
   }
 
   // ------------------------------------------------------------ teardown
+#ifdef IA2P_TC_TRACE
+  if (warp == 0) TRACE_PUT(8, gtime_ns());
+#endif
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();        // both CTAs done with TMEM / no remote arrive in flight
   if (warp == 1) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+#ifdef IA2P_TC_TRACE
+  if (threadIdx.x == 0 && g_tc_timeline != nullptr) atomicMax(g_tc_timeline + 2 * (size_t)p.trace_id + 1, gtime_ns());
+#endif
 }
 
 // ================================================================ host side
@@ -775,29 +845,36 @@ static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+#ifdef IA2P_TC_TRACE
+  p.trace_id = g_tc_launch_id++;
+#endif
   IA2P_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG, EPI>, maps, p));
   IA2P_LAUNCH_CHECK();
   return 0;
 }
 
-// CTA-pair (cta_group::2) variant: measured on B200 (profiles/README.md) it matches the single-CTA kernel within +-4 % --
-// the single-CTA main loop already keeps the tensor pipe ~81 % active at the power-capped clock -- so the simpler kernel is the
-// default and IA2P_GEMM_CG=2 selects the pair kernel (kept: it halves the L2->smem operand traffic and frees smem for a
-// TMA-staged epilogue).
-static int gemm_cg_override() {
+// CTA-pair (cta_group::2) kernel is the default: it halves the L2->smem traffic of the B operand (48 -> 32 KB per CTA and
+// k-block), which is what bounds the single-CTA main loop (~15 TB/s of L2->SM reads at 128x256 tiles, profiles/README.md); in the
+// power-capped full step it is worth ~1-2 %.  Tiles with a short main loop (K <= 768) stay on the single-CTA kernel: the pair
+// protocol's per-tile hand-offs (remote tmem_empty arrives, multicast commits) cost more than the B traffic saves there
+// (measured: M 32768, N 5120, K 640 GEGLU 653 -> 535 TFLOP/s with pairs).  IA2P_GEMM_CG=1 / 2 force one kernel (experiments).
+static bool use_pair(int m_tiles, int num_kb) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("IA2P_GEMM_CG");
-    v = (e != nullptr && e[0] == '2') ? 2 : 1;
+    v = (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '2') ? 2 : 0;
   }
-  return v;
+  if (m_tiles < 2) return false;
+  return v == 2 || (v == 0 && num_kb > 12);
 }
 
 // fp32 outputs go through the TMA-store epilogue (EPI = 1); IA2P_GEMM_EPI=0 forces the register-store epilogue (experiments)
@@ -822,7 +899,7 @@ static bool tma_residual(const TcParams& p) {
 
 template <int BN>
 static int dispatch_bn(const TcMaps& maps, TcParams& p, cudaStream_t st) {
-  const bool pair = gemm_cg_override() == 2 && p.m_tiles >= 2;
+  const bool pair = use_pair(p.m_tiles, p.num_kb);
   if (tma_residual(p)) return pair ? launch_tc<BN, 2, 2>(maps, p, st) : launch_tc<BN, 1, 2>(maps, p, st);
   if (tma_epilogue(p)) return pair ? launch_tc<BN, 2, 1>(maps, p, st) : launch_tc<BN, 1, 1>(maps, p, st);
   return pair ? launch_tc<BN, 2, 0>(maps, p, st) : launch_tc<BN, 1, 0>(maps, p, st);
@@ -859,7 +936,7 @@ static int dispatch_tc(TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
 }
 
 static int make_w_map(TcMaps& maps, const void* W, int64_t N, int64_t Ktot, int bn, int m_tiles) {
-  const bool pair = gemm_cg_override() == 2 && m_tiles >= 2;      // must mirror dispatch_tc: a CTA of a pair loads BN/2 rows
+  const bool pair = use_pair(m_tiles, (int)(Ktot / 64));          // must mirror dispatch_bn: a CTA of a pair loads BN/2 rows
   const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
   const uint64_t str[2] = {1, (uint64_t)Ktot};
   const uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
@@ -877,6 +954,19 @@ static int ilog2_exact(int v) {
 }  // namespace ia2p
 
 using namespace ia2p;
+
+#ifdef IA2P_TC_TRACE
+extern "C" int ia2p_debug_set_timeline(void* dev_buffer) {    // also resets the launch-id counter; returns nothing useful
+  unsigned long long* p = static_cast<unsigned long long*>(dev_buffer);
+  g_tc_launch_id = 0;
+  return (int)cudaMemcpyToSymbol(g_tc_timeline, &p, sizeof(p));
+}
+extern "C" int ia2p_debug_next_launch_id(void) { return g_tc_launch_id; }
+extern "C" int ia2p_debug_set_trace(void* dev_buffer) {       // debug build only; not part of include/ia2p.h
+  unsigned long long* p = static_cast<unsigned long long*>(dev_buffer);
+  return (int)cudaMemcpyToSymbol(g_tc_trace, &p, sizeof(p));
+}
+#endif
 
 extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                               const void* W, void* out, int64_t ldo, int64_t M, int64_t N,

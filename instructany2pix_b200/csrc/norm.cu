@@ -38,6 +38,8 @@ constexpr int kGnMaxSlabs = 128;
 template <typename T>
 __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
                                 long long hw, int groups, int pix_per_slab, double* __restrict__ partials) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   extern __shared__ float sm[];   // [ROWS][2][C]
   const int C = ca + cb;
   const int c0 = threadIdx.x * 8;
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const T* __restrict__ 
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw, long long hw, int groups,
                                 float eps, int silu, int pix_per_slab, const double* __restrict__ partials) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   extern __shared__ float sm[];   // scale[C], shift[C], then mean[groups], rstd[groups]
   const int C = ca + cb;
   const int cpg = C / groups;
@@ -179,6 +183,8 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const T* __restrict__ 
 template <typename T, typename TO, int MAXV>
 __global__ void layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  TO* __restrict__ y, long long rows, int cols, float eps) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -228,9 +234,9 @@ static int launch_ln(const void* x, const float* gamma, const float* beta, void*
   const long long grid = (rows * 32 + block - 1) / block;
   const T* xp = static_cast<const T*>(x);
   TO* yp = static_cast<TO*>(y);
-  if (cols <= 8 * 32 * 2) layernorm_kernel<T, TO, 2><<<(unsigned)grid, block, 0, st>>>(xp, gamma, beta, yp, rows, (int)cols, eps);
-  else if (cols <= 8 * 32 * 5) layernorm_kernel<T, TO, 5><<<(unsigned)grid, block, 0, st>>>(xp, gamma, beta, yp, rows, (int)cols, eps);
-  else layernorm_kernel<T, TO, 8><<<(unsigned)grid, block, 0, st>>>(xp, gamma, beta, yp, rows, (int)cols, eps);
+  if (cols <= 8 * 32 * 2) launch_pdl(layernorm_kernel<T, TO, 2>, dim3((unsigned)grid), dim3(block), 0, st, xp, gamma, beta, yp, rows, (int)cols, eps);
+  else if (cols <= 8 * 32 * 5) launch_pdl(layernorm_kernel<T, TO, 5>, dim3((unsigned)grid), dim3(block), 0, st, xp, gamma, beta, yp, rows, (int)cols, eps);
+  else launch_pdl(layernorm_kernel<T, TO, 8>, dim3((unsigned)grid), dim3(block), 0, st, xp, gamma, beta, yp, rows, (int)cols, eps);
   IA2P_LAUNCH_CHECK();
   return 0;
 }
@@ -274,14 +280,14 @@ extern "C" int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, i
   __nv_bfloat16* rp = static_cast<__nv_bfloat16*>(raw);
   if (x_dtype == IA2P_BF16) {
     const __nv_bfloat16 *a = static_cast<const __nv_bfloat16*>(xa), *b = static_cast<const __nv_bfloat16*>(xb);
-    gn_stats_kernel<<<grid, block, smem_stats, st>>>(a, (int)ca, b, (int)cb, hw, groups, pps, stats);
+    launch_pdl(gn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(block), smem_stats, st, a, (int)ca, b, (int)cb, hw, groups, pps, stats);
     IA2P_LAUNCH_CHECK();
-    gn_apply_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
+    launch_pdl(gn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(block), smem, st, a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
   } else {
     const float *a = static_cast<const float*>(xa), *b = static_cast<const float*>(xb);
-    gn_stats_kernel<<<grid, block, smem_stats, st>>>(a, (int)ca, b, (int)cb, hw, groups, pps, stats);
+    launch_pdl(gn_stats_kernel<float>, dim3(grid), dim3(block), smem_stats, st, a, (int)ca, b, (int)cb, hw, groups, pps, stats);
     IA2P_LAUNCH_CHECK();
-    gn_apply_kernel<<<grid, block, smem, st>>>(a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
+    launch_pdl(gn_apply_kernel<float>, dim3(grid), dim3(block), smem, st, a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
   }
   IA2P_LAUNCH_CHECK();
   return 0;

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(128)
 gemm_smallm_kernel(const float* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ W,
                    const float* __restrict__ bias, const float* __restrict__ residual, long long ldr,
                    float* __restrict__ out, long long ldo, int M, int N, int K, int act_in, int act) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int n0 = blockIdx.x * 32 + warp * 8;
@@ -98,6 +100,8 @@ gemm_smallm_kernel(const float* __restrict__ A, long long lda, const __nv_bfloat
 
 // grid (heads, batch); block (32, T): warp i = query i, lane l = head dims (2l, 2l+1)
 __global__ void causal_attn_small_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int E) {
+  pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int i = threadIdx.y, lane = threadIdx.x;
   const int h = blockIdx.x;
   const long long b = blockIdx.y;

@@ -22,6 +22,7 @@ def _stream():
 # PROFILE, when a list, receives (symbol, flops, start_event, end_event) for every C-ABI call made in eager mode.
 LAUNCHES = 0
 PROFILE = None
+TAG_ALWAYS = False          # tools/timeline_step.py: build the shape tags without event profiling
 _KERNELS_PER_CALL = {"ia2p_groupnorm_nhwc": 2}
 _FLOPS = 0.0
 _TAG = ""
@@ -249,7 +250,7 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
         ln_parts = ln_stats.shape[1]
     global _FLOPS, _TAG
     _FLOPS = 2.0 * M * N * (K1 + K2)
-    if PROFILE is not None:
+    if PROFILE is not None or TAG_ALWAYS:
         _TAG = (f"gemm M{M} N{N} K{K1 + K2}{' geglu' if geglu else ''}{' res' + str(residual.dtype)[6:] if residual is not None else ''}"
                 f" out{str(out.dtype)[6:]}{' +ln_stats' if want_ln else ''}{' ln_fold' if ln is not None else ''}")
     _run(lib.ia2p_gemm_ln_bf16, (a.data_ptr(), lda, K1, _ptr(a2), lda2, K2, w.data_ptr(), out.data_ptr(), ldo, M, N,
@@ -290,7 +291,7 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
     bias, rowbias = _f32(bias, "bias"), _f32(rowbias, "rowbias")
     global _FLOPS, _TAG
     _FLOPS = 2.0 * B * Ho * Wo * cout * w.shape[1]
-    if PROFILE is not None:
+    if PROFILE is not None or TAG_ALWAYS:
         _TAG = f"conv {H}x{W} C{Cin}->{cout} K{w.shape[1]} s{stride}{' res' if residual is not None else ''} out{str(out_dtype)[6:]}"
     _run(lib.ia2p_conv3x3_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, stride, w.data_ptr(), _ptr(sc_a), ca, _ptr(sc_b), cb,
                                           out.data_ptr(), _DT[out_dtype], cout, _ptr(bias), _ptr(rowbias), _ptr(residual),

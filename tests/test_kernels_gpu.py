@@ -136,6 +136,24 @@ def test_gemm_geglu(M, C):
     assert rel(out, ref) < TOL
 
 
+def test_gelu_accuracy():
+    """the epilogue's exact-GELU evaluation (A&S 7.1.26) against torch's erf GELU in fp64, through a GEGLU GEMM whose value
+    half is the constant 1 and whose gate half sweeps [-10, 10]: |error| must stay below bf16 output rounding (2^-9 rel)."""
+    from instructany2pix_b200.packing import interleave_geglu
+    M, C = 256, 64
+    a = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    a[:, 0] = 1.0
+    w = torch.zeros(8 * C, C, device=DEV, dtype=torch.bfloat16)            # rows [0,4C) value, [4C,8C) gate
+    g = torch.linspace(-10, 10, 4 * C, device=DEV).to(torch.bfloat16)
+    w[:4 * C, 0] = 1.0
+    w[4 * C:, 0] = g
+    b = torch.zeros(8 * C, device=DEV)
+    wi, bi = interleave_geglu(w, b)
+    out = ops.gemm(a, wi, bias=bi, geglu=True).float()
+    ref = F.gelu(g.double()).float().expand(M, -1)
+    assert ((out - ref).abs() <= 2 ** -8 * ref.abs() + 1e-6).all()
+
+
 def _conv_ref(x, w, stride=1):
     return F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=stride, padding=1).permute(0, 2, 3, 1)
 
