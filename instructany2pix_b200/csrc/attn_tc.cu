@@ -3,12 +3,15 @@
 // CTA = 128 query rows of one (batch, head); 6 warps: w0 TMA producer, w1 tcgen05.mma issuer (owns TMEM), w2..w5 softmax
 // (one query row per thread, so row max / row sum need no shuffles).  Per 128-key block j:
 //   MMA1: S(TMEM, 128 cols fp32) = Q(smem) K_j^T(smem)                      [M128 N128 K64]
-//   softmax warps: S -> registers (2 passes over TMEM), p = exp2(s*scale - m_ref) -> bf16 -> smem (K-major SW128 A operand)
-//   MMA2: O(TMEM, 64 cols fp32) += P(smem) V_j(smem, MN-major)               [M128 N64 K128]
+//   softmax warps: S -> registers (chunk loads software-pipelined against the exp math), p = exp2(s*scale - m_ref) -> bf16
+//                  -> TMEM (64 columns, two keys per 32-bit cell: the A operand of MMA2 is read straight from TMEM)
+//   MMA2: O(TMEM, 64 cols fp32) += P(TMEM) V_j(smem, MN-major)               [M128 N64 K128]
 // O accumulates in TMEM across blocks; the running reference max m_ref is only raised (and O, l rescaled through
 // tcgen05.ld/st) when a row's block max exceeds it by more than 8 (log2 units), so the rescale path is rare and the
 // result is exact up to the common factor that cancels in O / l.  MMA1 of block j+1 is issued before MMA2 of block j, and
-// two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each), so tensor work overlaps the softmax math.
+// two CTAs are co-resident per SM (80 KB smem, 256 TMEM columns each), so tensor work overlaps the softmax math.
+// (Round-1 history: P used to go through shared memory -- 16 swizzled 16-byte stores per thread + fence.proxy.async cost
+// 450 of the 2 700 cycles a key block took, tools/trace_attn.py; keeping P in TMEM removes that and 32 KB of smem.)
 #include <cuda.h>
 
 #include <mutex>
@@ -22,9 +25,19 @@ struct alignas(64) FaMaps {
 };
 
 constexpr int kFaTile = 128 * 128;                 // bytes: 128 rows x 64 bf16
-constexpr int kFaSmemTiles = kFaTile * (1 + 2 + 2 + 2);   // Q, K x2, V x2, P (two 64-key halves)
+constexpr int kFaSmemTiles = kFaTile * (1 + 2 + 2);       // Q, K x2, V x2
 constexpr int kFaSmemBytes = kFaSmemTiles + 1024;  // barriers live in the alignment slack in front of the tiles
 constexpr float kRescaleThreshold = 8.0f;
+// What bounds this kernel (measured, tools/trace_attn.py + ncu): per 128 x 128 key block the softmax warps must read 64 KB of S
+// from TMEM (tcgen05.ld: 64 B/clk per SM -> 1024 cycles) and evaluate 16 384 exponentials on the 16 SFU lanes of the SM (1024
+// cycles), while the two MMAs need 512 cycles at head_dim 64: the tensor pipe cannot exceed ~50 %.  The kernel runs a block in
+// ~1 200 cycles per SM (two co-resident CTAs at ~2 400 each), i.e. ~85 % of that TMEM/SFU floor.  Tried and dropped because
+// they did not move it: bf16 packing by truncation instead of F2FP, and evaluating every 4th exp2 on the FMA pipe with a
+// polynomial (FlashAttention-4 style) -- the latter made the block slower (2 435 -> 2 751 cycles).
+#ifdef IA2P_TC_TRACE
+#define IA2P_TRACE_BUF g_fa_trace
+__device__ unsigned long long* g_fa_trace = nullptr;           // debug build: counters of the CTAs with blockIdx.y == z == 0
+#endif
 
 __global__ void __launch_bounds__(192, 2)
 fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ out, long long ldo, int n_tokens, float scale_log2) {
@@ -33,7 +46,7 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 128u + 1023u) & ~1023u;       // >= 128 B of barriers in front
   if (tiles + kFaSmemTiles > raw + kFaSmemBytes) __trap();    // dynamic smem base less aligned than assumed
-  const uint32_t sQ = tiles, sK = sQ + kFaTile, sV = sK + 2 * kFaTile, sP = sV + 2 * kFaTile;
+  const uint32_t sQ = tiles, sK = sQ + kFaTile, sV = sK + 2 * kFaTile;
   const uint32_t bars = raw;
   const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, k_empty = bars + 40, v_empty = bars + 56;
   const uint32_t s_full = bars + 72, s_empty = bars + 80, p_full = bars + 88, pv_full = bars + 96, tmem_slot = bars + 104;
@@ -57,7 +70,7 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;   // S 128 | O 64 | P 64 (bf16 pairs) columns
   pdl_wait();                // barrier init / TMEM allocation above overlapped the previous kernel's tail
 
   if (warp == 0) {
@@ -85,10 +98,19 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);
+    TRACE_DECL(tr_wait_k);
+    TRACE_DECL(tr_wait_sempty);
+    TRACE_DECL(tr_wait_v);
+    TRACE_DECL(tr_wait_p);
+    TRACE_T0(tl0);
     auto issue_qk = [&](int j) {
       const int st = j & 1;
+      TRACE_T0(ta);
       mbar_wait(k_full + 8 * st, (uint32_t)((j >> 1) & 1));
+      TRACE_ADD(tr_wait_k, ta);
+      TRACE_T0(tb);
       if (j > 0) mbar_wait(s_empty, (uint32_t)((j - 1) & 1));     // softmax finished reading S_{j-1}
+      TRACE_ADD(tr_wait_sempty, tb);
       tc_fence_after();
       if (lane == 0) {
         const uint64_t da = umma_desc_sw128(sQ), db = umma_desc_sw128(sK + st * kFaTile);
@@ -104,29 +126,45 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
     for (int j = 0; j < n_blocks; ++j) {
       if (j + 1 < n_blocks) issue_qk(j + 1);                      // overlaps the softmax of block j
       const int st = j & 1;
+      TRACE_T0(tc);
       mbar_wait(v_full + 8 * st, (uint32_t)((j >> 1) & 1));
+      TRACE_ADD(tr_wait_v, tc);
+      TRACE_T0(td);
       mbar_wait(p_full, (uint32_t)(j & 1));                       // P_j in smem; O (TMEM) rescaled if needed
+      TRACE_ADD(tr_wait_p, td);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {                          // 8 x 16 keys
-          const uint64_t da = umma_desc_sw128(sP + (ks >> 2) * kFaTile) + (uint64_t)(2 * (ks & 3));
+        for (int ks = 0; ks < 8; ++ks) {                          // 8 x 16 keys = 8 TMEM columns of P each
           const uint64_t db = umma_desc_sw128_mn(sV + st * kFaTile + ks * 2048, kFaTile);
-          umma_bf16(tO, da, db, idesc_pv, (uint32_t)((j | ks) != 0));
+          umma_bf16_ts(tO, tP + (uint32_t)(ks * 8), db, idesc_pv, (uint32_t)((j | ks) != 0));
         }
         umma_commit(v_empty + 8 * st);
         umma_commit(pv_full);
       }
       __syncwarp();
     }
+#ifdef IA2P_TC_TRACE
+    if (blockIdx.y == 0 && blockIdx.z == 0) {
+      TRACE_PUT(0, tr_wait_k); TRACE_PUT(1, tr_wait_sempty); TRACE_PUT(2, tr_wait_v); TRACE_PUT(3, tr_wait_p);
+      TRACE_PUT(4, clock64() - tl0); TRACE_PUT(9, n_blocks);
+    }
+#endif
   } else {
     // ------------------------------------------------------------ softmax / epilogue: one query row per thread
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     float m_ref = -INFINITY, l = 0.f;
+    TRACE_DECL(tr_wait_s);
+    TRACE_DECL(tr_softmax);
+    TRACE_DECL(tr_wait_pv);
+    TRACE_DECL(tr_pwrite);
     for (int j = 0; j < n_blocks; ++j) {
+      TRACE_T0(ts0);
       mbar_wait(s_full, (uint32_t)(j & 1));
+      TRACE_ADD(tr_wait_s, ts0);
+      TRACE_T0(ts1);
       tc_fence_after();
       const int kv_left = n_tokens - j * 128;                     // valid keys in this block (>= 1)
       const bool ragged = kv_left < 128;                          // only the last block can be ragged
@@ -137,19 +175,36 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       // raised when a row's block sum shows it is stale by > 2^20 (or on the first / ragged block) -> SLOW PATH below.
       bool slow = (j == 0) || ragged;
       if (!slow) {
+        // chunk c + 1 is in flight from TMEM while the exponentials of chunk c are computed
+        uint32_t va[32], vb[32];
+        float ls0 = 0.f, ls1 = 0.f;
+        const float neg_m = -m_ref;
+        auto soft32 = [&](const uint32_t (&v)[32], int c) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
-            lsum += p0 + p1;
+          for (int i = 0; i < 32; i += 4) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, neg_m));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, neg_m));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(v[i + 2]), scale_log2, neg_m));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(v[i + 3]), scale_log2, neg_m));
+            ls0 += p0 + p2;
+            ls1 += p1 + p3;
             pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+            pk[c * 16 + (i >> 1) + 1] = pack_bf16x2(p2, p3);
           }
-        }
+        };
+        tmem_ld_32x32(tS + lane_sel, va);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + lane_sel + 32u, vb);
+        soft32(va, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + lane_sel + 64u, va);
+        soft32(vb, 1);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + lane_sel + 96u, vb);
+        soft32(va, 2);
+        tmem_ld_wait();
+        soft32(vb, 3);
+        lsum = ls0 + ls1;
         slow = !(lsum < 1048576.f);                               // also catches inf / nan
       }
       const bool any_slow = __any_sync(0xffffffffu, slow);
@@ -192,6 +247,8 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);                        // S may be overwritten by MMA1 of block j+1
+      TRACE_ADD(tr_softmax, ts1);
+      TRACE_T0(ts2);
       // P buffer / O accumulator are free once MMA2 of block j-1 has completed
       if (j > 0) {
         mbar_wait(pv_full, (uint32_t)((j - 1) & 1));
@@ -209,19 +266,26 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
           tmem_st_wait();
         }
       }
-      // write P (K-major, SWIZZLE_128B, two 64-key halves): row r, 16-byte chunk c -> r*128 + ((c ^ (r&7)) << 4)
-      uint8_t* pbase = smem_raw + (sP - raw);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int half = c >> 3, cc = c & 7;
-        *reinterpret_cast<uint4*>(pbase + half * kFaTile + row * 128 + ((cc ^ (row & 7)) << 4)) =
-            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      TRACE_ADD(tr_wait_pv, ts2);
+      TRACE_T0(ts3);
+      // P -> TMEM: this thread's row, 64 cells of two bf16 keys each (the A operand of MMA2)
+      {
+        uint32_t (&plo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
+        uint32_t (&phi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
+        tmem_st_32x32(tP + lane_sel, plo);
+        tmem_st_32x32(tP + lane_sel + 32u, phi);
+        tmem_st_wait();
       }
-      fence_proxy_async();                                        // generic-proxy smem writes -> visible to the MMA (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      TRACE_ADD(tr_pwrite, ts3);
     }
+#ifdef IA2P_TC_TRACE
+    if (blockIdx.y == 0 && blockIdx.z == 0 && warp == 2) {
+      TRACE_PUT(5, tr_wait_s); TRACE_PUT(6, tr_softmax); TRACE_PUT(7, tr_wait_pv); TRACE_PUT(8, tr_pwrite);
+    }
+#endif
     // epilogue: O / l -> bf16 -> global (one 128-byte row per thread)
     mbar_wait(pv_full, (uint32_t)((n_blocks - 1) & 1));
     tc_fence_after();
@@ -283,6 +347,13 @@ static int fa_make_map(CUtensorMap* m, const void* base, int64_t cols, int64_t l
   IA2P_REQUIRE(r == CUDA_SUCCESS, IA2P_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
   return 0;
 }
+
+#ifdef IA2P_TC_TRACE
+extern "C" int ia2p_debug_set_fa_trace(void* dev_buffer) {
+  unsigned long long* p = static_cast<unsigned long long*>(dev_buffer);
+  return (int)cudaMemcpyToSymbol(g_fa_trace, &p, sizeof(p));
+}
+#endif
 
 int launch_fa_tc(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int64_t batch,
                  int64_t n_tokens, int heads, float softmax_scale, cudaStream_t st) {

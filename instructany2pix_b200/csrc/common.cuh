@@ -123,6 +123,27 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---------------------------------------------------------------- debug-build tracing (tools/trace_gemm.py, -DIA2P_TC_TRACE)
+#ifdef IA2P_TC_TRACE
+// each .cu that traces defines its own `__device__ unsigned long long* IA2P_TRACE_BUF` (no relocatable device code here)
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE_DECL(name) long long name = 0
+#define TRACE_T0(v) const long long v = clock64()
+#define TRACE_ADD(acc, v) acc += clock64() - v
+#define TRACE_PUT_AT(cta, slot, val) do { if (IA2P_TRACE_BUF != nullptr && lane == 0) IA2P_TRACE_BUF[(size_t)(cta) * 16 + (slot)] = (unsigned long long)(val); } while (0)
+#define TRACE_PUT(slot, val) TRACE_PUT_AT(blockIdx.x, slot, val)
+#else
+#define TRACE_DECL(name)
+#define TRACE_T0(v)
+#define TRACE_ADD(acc, v)
+#define TRACE_PUT_AT(cta, slot, val)
+#define TRACE_PUT(slot, val)
+#endif
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -285,6 +306,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with the A operand in TMEM (lane = row, each 32-bit column holds two consecutive K elements): D (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Arrive on an mbarrier when all tcgen05 ops previously issued by this thread have completed.

@@ -64,24 +64,10 @@ struct TcParams {
 };
 
 #ifdef IA2P_TC_TRACE
-// Debug build only (tools/trace_gemm.py): per-CTA wait/busy cycle counters of the three warp roles.
+#define IA2P_TRACE_BUF g_tc_trace
 __device__ unsigned long long* g_tc_trace = nullptr;
-__device__ unsigned long long* g_tc_timeline = nullptr;        // [launch id][2] = {min start, max end} (globaltimer ns)
+__device__ unsigned long long* g_tc_timeline = nullptr;
 static int g_tc_launch_id = 0;                                 // host: id handed to the next launch (fixed per graph node)
-__device__ __forceinline__ unsigned long long gtime_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-#define TRACE_DECL(name) long long name = 0
-#define TRACE_T0(v) const long long v = clock64()
-#define TRACE_ADD(acc, v) acc += clock64() - v
-#define TRACE_PUT(slot, val) do { if (g_tc_trace != nullptr && lane == 0) g_tc_trace[(size_t)blockIdx.x * 16 + (slot)] = (unsigned long long)(val); } while (0)
-#else
-#define TRACE_DECL(name)
-#define TRACE_T0(v)
-#define TRACE_ADD(acc, v)
-#define TRACE_PUT(slot, val)
 #endif
 
 struct TcItem { int m_unit, n_tile, n_off, w; };
