@@ -135,6 +135,24 @@ def build_models(dev, want_prior):
     return unet, prior
 
 
+def build_vae(dev):
+    """SDXL AutoencoderKL decoder (random init of the named architecture) for the end-to-end leg: latents -> images."""
+    from instructany2pix_b200.vae import B200VAE
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    vae = B200VAE(device=dev, with_encoder=False)
+    for name, p in vae.named_parameters():
+        if p.ndim >= 2:
+            fan_in = p[0].numel()
+            p.copy_(((torch.rand(p.shape, generator=g, device=dev) * 2 - 1) * fan_in ** -0.5).to(p.dtype))
+        elif name.endswith("weight"):
+            p.fill_(1.0)
+        else:
+            p.zero_()
+    vae.invalidate()
+    return vae
+
+
 def host_inputs(B, L, seed):
     """Synthetic per-request conditioning in PINNED host memory: what a caller of the public API holds."""
     g = torch.Generator()
@@ -283,6 +301,7 @@ def main():
     from instructany2pix_b200.sampler import B200Sampler
     L, B, NS = wl["L"], wl["B"], args.num_inference_steps
     unet, prior = build_models(dev, wl["prior"])
+    vae = build_vae(dev)
     sampler = B200Sampler(unet, use_cuda_graph=not args.no_graph)
     host = host_inputs(B, L, seed=1000 + rank)                   # every rank samples different prompts/seeds
     dev_in = {k: v.to(dev) for k, v in host.items()}
@@ -294,7 +313,8 @@ def main():
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 1)):
-        run_trajectory(sampler, prior, dev_in, NS)
+        lat_w = run_trajectory(sampler, prior, dev_in, NS)
+    vae.decode(lat_w)                                            # warm-up of the decode path (function attributes, allocator)
     # ---- device-resident timing (value)
     sync_all()
     clocks = ClockSampler(local)
@@ -317,10 +337,14 @@ def main():
     for _ in range(args.steps):
         cur = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         out = run_trajectory(sampler, prior, cur, NS)
-        res = out.to("cpu")                                      # device -> host read of the final latents (syncs)
+        v0 = torch.cuda.Event(enable_timing=True)
+        v0.record()
+        img = vae.decode(out)                                    # sdxl_pipeline.py:859-871: latents -> (B,3,8L,8L) images
+        res = img.to("cpu")                                      # device -> host read of the decoded images (syncs)
     f1.record()
     sync_all()
     ms_e2e = f0.elapsed_time(f1)
+    ms_decode = v0.elapsed_time(f1)                              # last step's decode + image read-back
     d2h = res.numel() * res.element_size()
     if world > 1:
         tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -362,7 +386,9 @@ def main():
                            l2_policy="inputs larger than L2 (5.8 GB weights + activations stream every step); no explicit flush",
                            cuda_graph=not args.no_graph, residual_stream="fp32"),
                unet_step_ms=unet_step_ms, unet_tensor_frac=whole_frac, clocks=clk,
-               e2e=dict(value=e2e_value, unit="images/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+               e2e=dict(value=e2e_value, unit="images/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                        includes="H2D of the conditioning + noise, 50-step trajectory, VAE decode to fp32 images, D2H of the images",
+                        vae_decode_and_readback_ms=ms_decode),
                gpu_launches=int(gpu_launches), roofline=roof)
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

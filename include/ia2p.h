@@ -48,6 +48,17 @@ int ia2p_cfg_ddim_step(const void* eps2, int eps_dtype, const void* x, void* x_o
 int ia2p_axpby(const void* eps, int eps_dtype, const void* x, void* x_out, int x_dtype, int64_t n,
                float c_x, float c_e, void* stream);
 
+/* Start-latent blend: out = ll/|ll| * (alpha|x| + (1-alpha)|y|), ll = alpha x + (1-alpha) y, norms over all n elements, fp32.
+ * Replaces InstructAny2PixPipeline.polar_intrtpolate, pipeline.py:295-300 (call site :332-336: inverted latent vs fresh noise).
+ * workspace: ia2p_polar_workspace_bytes() bytes of device memory (per-block partial sums; bit-reproducible, no atomics). */
+int64_t ia2p_polar_workspace_bytes(void);
+int ia2p_polar_interpolate(const float* x, const float* y, float* out, int64_t n, float alpha, void* workspace, void* stream);
+
+/* out[b,c,p] = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise), moments = [B, 2C, HW] (mean | logvar), fp32.
+ * Replaces [3P] DiagonalGaussianDistribution.sample() * scaling_factor at ddim/pnp_pipeline.py:201-204.  noise NULL -> the mode. */
+int ia2p_gaussian_sample(const float* moments, const float* noise, float* out, int64_t B, int64_t C, int64_t HW, float scale,
+                         void* stream);
+
 /* Prior: x0->eps transform + CFG (cond half FIRST) + DDPM ancestral step, fp32.
  * Replaces prior/model.py:641-648 (get_eps :208-239, CFG :643-644, [3P] DDPMScheduler.step).
  * x0_pair: [2, n] = model output for (cond, uncond); x: [n]; noise: [n] or NULL (sigma ignored). */
@@ -126,16 +137,31 @@ int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64
                            void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
                            const void* residual, int res_dtype, void* stream);
 
+/* Stride-2 3x3 conv with padding only at the bottom / right (input index 2*o + k): the VAE encoder's Downsample2D
+ * ([3P] diffusers: padding=0 after F.pad(x, (0,1,0,1)); reached from vae.encode at ddim/pnp_pipeline.py:195-204). */
+int ia2p_conv3x3_s2_padend_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w,
+                                     void* out, int out_dtype, int64_t Cout, const float* bias, void* stream);
+
 /* conv_in: 3x3 pad 1 conv from NCHW (fp32|bf16|fp16, few channels) to NHWC (bf16|fp32).  w fp32 [Cout,Cin,3,3].
  * The input batch is read modulo `in_batch` (CFG duplication without cat([x]*2): custom_pipelines.py:332). */
 int ia2p_conv_in_nchw(const void* x, int x_dtype, int64_t in_batch, int64_t B, int64_t H, int64_t W, int64_t Cin,
                       const float* w, const float* bias, void* out, int out_dtype, int64_t Cout, void* stream);
-/* conv_out: 3x3 pad 1 conv from NHWC bf16 to NCHW (fp32|bf16|fp16), few output channels (<= 8).
+/* conv_out: 3x3 pad 1 conv from NHWC bf16 to NCHW (fp32|bf16|fp16), Cout in {3, 4, 8} (UNet eps, VAE image, VAE moments).
  * w fp32 [Cout,3,3,Cin] (K order ky,kx,cin). */
 int ia2p_conv_out_nhwc(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin,
                        const float* w, const float* bias, void* out, int out_dtype, int64_t Cout, void* stream);
 
+/* 1x1 conv over <= 8 channels, NCHW fp32 -> NCHW fp32: out = scale * (w x) + bias.  Replaces [3P] AutoencoderKL.post_quant_conv
+ * / quant_conv with the latent (un)scaling of ddim/sdxl_pipeline.py:866 and pnp_pipeline.py:204 folded into `scale`. */
+int ia2p_conv1x1_nchw_small(const float* x, const float* w, const float* bias, float* out, int64_t B, int64_t Cin,
+                            int64_t Cout, int64_t HW, float scale, void* stream);
+
 /* ---------------------------------------------------------------- attention */
+
+/* p = softmax(scale * scores) per row, fp32 [rows, cols] (pitch ld) -> bf16 (pitch ldo).  Middle step of the VAE's single-head,
+ * 512-wide attention ([3P] AutoencoderKL mid_block.attentions.0: one SDPA over L*L tokens), run as GEMM -> softmax -> GEMM. */
+int ia2p_softmax_rows_f32_bf16(const float* scores, int64_t ld, void* out, int64_t ldo, int64_t rows, int64_t cols,
+                               float scale, void* stream);
 
 /* Flash self-attention, head_dim 64, non-causal.  Replaces F.scaled_dot_product_attention at
  * attention_processor.py:259-261.  q/k/v: bf16, token (b*N + i) row at ptr + row*ld, head h at cols [64h, 64h+64). */

@@ -24,6 +24,8 @@ SIGNATURES = {
     "ia2p_device_check": ([_i], _i),
     "ia2p_cfg_ddim_step": ([_p, _i, _p, _p, _i, _p, _i, _l, _l, _f, _f, _f, _p], _i),
     "ia2p_axpby": ([_p, _i, _p, _p, _i, _l, _f, _f, _p], _i),
+    "ia2p_polar_workspace_bytes": ([], _l),
+    "ia2p_polar_interpolate": ([_p, _p, _p, _l, _f, _p, _p], _i),
     "ia2p_prior_cfg_ddpm_step": ([_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _p], _i),
     "ia2p_timestep_embedding": ([_p, _l, _i, _i, _f, _p, _i, _p], _i),
     "ia2p_upsample2x_nhwc": ([_p, _i, _p, _l, _l, _l, _l, _p], _i),
@@ -36,8 +38,12 @@ SIGNATURES = {
                            _p, _l, _p, _p, _l, _p, _f, _p], _i),
     "ia2p_gemm_ln_parts": ([_l], _l),
     "ia2p_conv3x3_nhwc_bf16": ([_p, _l, _l, _l, _l, _i, _p, _p, _l, _p, _l, _p, _i, _l, _p, _p, _p, _i, _p], _i),
+    "ia2p_conv3x3_s2_padend_nhwc_bf16": ([_p, _l, _l, _l, _l, _p, _p, _i, _l, _p, _p], _i),
+    "ia2p_gaussian_sample": ([_p, _p, _p, _l, _l, _l, _f, _p], _i),
     "ia2p_conv_in_nchw": ([_p, _i, _l, _l, _l, _l, _l, _p, _p, _p, _i, _l, _p], _i),
     "ia2p_conv_out_nhwc": ([_p, _l, _l, _l, _l, _p, _p, _p, _i, _l, _p], _i),
+    "ia2p_conv1x1_nchw_small": ([_p, _p, _p, _p, _l, _l, _l, _l, _f, _p], _i),
+    "ia2p_softmax_rows_f32_bf16": ([_p, _l, _p, _l, _l, _l, _f, _p], _i),
     "ia2p_flash_self_attn_bf16": ([_p, _p, _p, _l, _p, _l, _l, _l, _i, _f, _p], _i),
     "ia2p_decoupled_cross_attn_bf16": ([_p, _l, _p, _p, _l, _i, _p, _p, _l, _i, _f, _p, _l, _l, _l, _i, _f, _p], _i),
     "ia2p_gemm_smallm": ([_p, _l, _p, _p, _p, _l, _p, _l, _l, _l, _l, _i, _i, _p], _i),

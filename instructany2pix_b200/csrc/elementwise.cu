@@ -53,6 +53,57 @@ __global__ void prior_step_kernel(const float* __restrict__ x0_pair, const float
   }
 }
 
+// ---------------------------------------------------------------- polar interpolation of two latents (pipeline.py:295-300)
+// out = ll / |ll| * (alpha |x| + (1 - alpha) |y|),  ll = alpha x + (1 - alpha) y;  norms over the WHOLE tensor.
+// Pass 1: per-block partial sums of x^2, y^2, ll^2 (fp64, fixed order -> bit-reproducible); pass 2: every block re-reduces the
+// partials in the same order and applies the scale.
+constexpr int kPolarMaxBlocks = 256;
+__global__ void __launch_bounds__(256) polar_partials_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n,
+                                                             float alpha, double* __restrict__ partials) {
+  pdl_launch_dependents();
+  pdl_wait();
+  float sx = 0.f, sy = 0.f, sl = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float a = x[i], b = y[i], l = a * alpha + b * (1.f - alpha);
+    sx += a * a;
+    sy += b * b;
+    sl += l * l;
+  }
+  __shared__ double red[3][8];
+  double dx = sx, dy = sy, dl = sl;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dx += __shfl_xor_sync(0xffffffffu, dx, o);
+    dy += __shfl_xor_sync(0xffffffffu, dy, o);
+    dl += __shfl_xor_sync(0xffffffffu, dl, o);
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = dx; red[1][w] = dy; red[2][w] = dl; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    partials[blockIdx.x * 3 + threadIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) polar_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                                          long long n, float alpha, const double* __restrict__ partials, int nparts) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_scale;
+  if (threadIdx.x == 0) {
+    double t[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < nparts; ++i)
+      for (int k = 0; k < 3; ++k) t[k] += partials[i * 3 + k];
+    const double target = sqrt(t[0]) * (double)alpha + sqrt(t[1]) * (double)(1.f - alpha);
+    s_scale = (float)(target / sqrt(t[2]));
+  }
+  __syncthreads();
+  const float sc = s_scale;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (x[i] * alpha + y[i] * (1.f - alpha)) * sc;
+}
+
 template <typename TO>
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, long long n, int dim, int flip, float shift,
                                           TO* __restrict__ out) {
@@ -217,6 +268,92 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, long long B
   }
 }
 
+// ---------------------------------------------------------------- VAE boundary helpers
+// 1x1 conv over few channels, NCHW fp32 -> NCHW fp32: out[b,co,p] = scale * sum_ci w[co,ci] x[b,ci,p] + bias[co]
+// ([3P] AutoencoderKL.post_quant_conv / quant_conv, with the 1/scaling_factor of sdxl_pipeline.py:866 folded into `scale`).
+__global__ void conv1x1_nchw_small_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                          float* __restrict__ out, long long B, int Cin, int Cout, long long HW, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * HW; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    float v[8];
+    for (int ci = 0; ci < Cin; ++ci) v[ci] = x[(b * Cin + ci) * HW + p];
+    for (int co = 0; co < Cout; ++co) {
+      float a = 0.f;
+      for (int ci = 0; ci < Cin; ++ci) a += w[co * Cin + ci] * v[ci];
+      out[(b * Cout + co) * HW + p] = a * scale + (bias ? bias[co] : 0.f);
+    }
+  }
+}
+
+__global__ void gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, float* __restrict__ out,
+                                       long long B, long long CHW, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * CHW; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / CHW, r = i - b * CHW;
+    const float mean = moments[b * 2 * CHW + r];
+    float v = mean;
+    if (noise != nullptr) v += expf(0.5f * fminf(fmaxf(moments[b * 2 * CHW + CHW + r], -30.f), 20.f)) * noise[i];
+    out[i] = v * scale;
+  }
+}
+
+// Row softmax of an fp32 score matrix [rows, cols] (row pitch ld) -> bf16 probabilities: p = softmax(scale * s).  One CTA per
+// row, three passes over the row (max, sum, write); the row (<= 64 KB) stays in L1/L2 between them.  Used by the VAE's single
+// 512-wide attention head (16 384 tokens at 1024^2), which runs once per image as GEMM -> softmax -> GEMM.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, long long ld, __nv_bfloat16* __restrict__ out,
+                                                           long long ldo, int cols, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float4* row = reinterpret_cast<const float4*>(s + blockIdx.x * ld);
+  const int nv = cols >> 2;
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row[i];
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[w] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m * scale_log2;
+  }
+  __syncthreads();
+  const float m = bcast;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row[i];
+    sum += exp2f(fmaf(v.x, scale_log2, -m)) + exp2f(fmaf(v.y, scale_log2, -m)) + exp2f(fmaf(v.z, scale_log2, -m)) +
+           exp2f(fmaf(v.w, scale_log2, -m));
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[w] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    bcast = 1.f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  uint2* orow = reinterpret_cast<uint2*>(out + blockIdx.x * ldo);
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row[i];
+    uint2 o;
+    o.x = pack_bf16x2(exp2f(fmaf(v.x, scale_log2, -m)) * inv, exp2f(fmaf(v.y, scale_log2, -m)) * inv);
+    o.y = pack_bf16x2(exp2f(fmaf(v.z, scale_log2, -m)) * inv, exp2f(fmaf(v.w, scale_log2, -m)) * inv);
+    orow[i] = o;
+  }
+}
+
 static int grid_for(long long work_items, int block) {
   long long g = (work_items + block - 1) / block;
   const long long cap = (long long)sm_count() * 16;
@@ -264,6 +401,21 @@ extern "C" int ia2p_axpby(const void* eps, int eps_dtype, const void* x, void* x
   DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX,
       (launch_pdl(axpby_kernel<TE, TX>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps), static_cast<const TX*>(x),
                                                   static_cast<TX*>(x_out), n, c_x, c_e))));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t ia2p_polar_workspace_bytes(void) { return (int64_t)kPolarMaxBlocks * 3 * sizeof(double); }
+
+extern "C" int ia2p_polar_interpolate(const float* x, const float* y, float* out, int64_t n, float alpha, void* workspace, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && y && out && workspace && n > 0, IA2P_E_ARG, "polar_interpolate: null pointer or empty shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int grid = grid_for(n, 256);
+  if (grid > kPolarMaxBlocks) grid = kPolarMaxBlocks;
+  double* parts = static_cast<double*>(workspace);
+  IA2P_CUDA(launch_pdl(polar_partials_kernel, dim3(grid), dim3(256), 0, st, x, y, (long long)n, alpha, parts));
+  IA2P_CUDA(launch_pdl(polar_apply_kernel, dim3(grid), dim3(256), 0, st, x, y, out, (long long)n, alpha, (const double*)parts, grid));
   IA2P_LAUNCH_CHECK();
   return 0;
 }
@@ -347,12 +499,53 @@ extern "C" int ia2p_conv_out_nhwc(const void* x, int64_t B, int64_t H, int64_t W
                                   const float* bias, void* out, int out_dtype, int64_t Cout, void* stream) {
   if (int e = check_device()) return e;
   IA2P_REQUIRE(x && w && out && B > 0 && H > 0 && W > 0, IA2P_E_ARG, "conv_out: bad arguments");
-  IA2P_REQUIRE(Cin % 8 == 0 && Cout == 4, IA2P_E_SHAPE, "conv_out: Cin%%8==0 and Cout==4 required (got %lld, %lld)", (long long)Cin, (long long)Cout);
+  IA2P_REQUIRE(Cin % 8 == 0 && (Cout == 4 || Cout == 3 || Cout == 8), IA2P_E_SHAPE,
+               "conv_out: Cin%%8==0 and Cout in {3, 4, 8} required (got %lld, %lld)", (long long)Cin, (long long)Cout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(B * H * W * 32, 256);
-  DISPATCH_DTYPE(out_dtype, TO,
-      (launch_pdl(conv_out_kernel<TO, 4>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), B, (int)H, (int)W, (int)Cin, w,
-                                                    bias, static_cast<TO*>(out))));
+#define IA2P_CONV_OUT(CO_)                                                                                                      \
+  DISPATCH_DTYPE(out_dtype, TO,                                                                                                 \
+      (launch_pdl(conv_out_kernel<TO, CO_>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), B, (int)H, (int)W, \
+                  (int)Cin, w, bias, static_cast<TO*>(out))))
+  if (Cout == 4) { IA2P_CONV_OUT(4); }
+  else if (Cout == 3) { IA2P_CONV_OUT(3); }
+  else { IA2P_CONV_OUT(8); }
+#undef IA2P_CONV_OUT
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_conv1x1_nchw_small(const float* x, const float* w, const float* bias, float* out, int64_t B, int64_t Cin,
+                                       int64_t Cout, int64_t HW, float scale, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && w && out && B > 0 && HW > 0, IA2P_E_ARG, "conv1x1_nchw_small: bad arguments");
+  IA2P_REQUIRE(Cin >= 1 && Cin <= 8 && Cout >= 1 && Cout <= 8, IA2P_E_SHAPE, "conv1x1_nchw_small: channel counts must be in [1, 8]");
+  IA2P_CUDA(launch_pdl(conv1x1_nchw_small_kernel, dim3(grid_for(B * HW, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, w, bias, out,
+                       (long long)B, (int)Cin, (int)Cout, (long long)HW, scale));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_gaussian_sample(const float* moments, const float* noise, float* out, int64_t B, int64_t C, int64_t HW,
+                                    float scale, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(moments && out && B > 0 && C > 0 && HW > 0, IA2P_E_ARG, "gaussian_sample: bad arguments");
+  IA2P_CUDA(launch_pdl(gaussian_sample_kernel, dim3(grid_for(B * C * HW, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), moments,
+                       noise, out, (long long)B, (long long)(C * HW), scale));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_softmax_rows_f32_bf16(const float* scores, int64_t ld, void* out, int64_t ldo, int64_t rows, int64_t cols,
+                                          float scale, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(scores && out && rows > 0 && cols > 0, IA2P_E_ARG, "softmax_rows: bad arguments");
+  IA2P_REQUIRE(cols % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+               IA2P_E_ALIGN, "softmax_rows: cols / pitches must be multiples of 4 and the bases 16 / 8-byte aligned");
+  IA2P_REQUIRE(rows < (1ll << 31), IA2P_E_SHAPE, "softmax_rows: too many rows");
+  IA2P_CUDA(launch_pdl(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, static_cast<cudaStream_t>(stream), scores, (long long)ld,
+                       static_cast<__nv_bfloat16*>(out), (long long)ldo, (int)cols, scale * 1.4426950408889634f));
   IA2P_LAUNCH_CHECK();
   return 0;
 }

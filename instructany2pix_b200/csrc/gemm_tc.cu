@@ -1034,10 +1034,10 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
   return dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int stride,
-                                      const void* w, const void* sc_a, int64_t sc_ca, const void* sc_b, int64_t sc_cb,
-                                      void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
-                                      const void* residual, int res_dtype, void* stream) {
+static int conv3x3_impl(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int stride, bool pad_end,
+                        const void* w, const void* sc_a, int64_t sc_ca, const void* sc_b, int64_t sc_cb,
+                        void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
+                        const void* residual, int res_dtype, void* stream) {
   if (int e = check_device()) return e;
   IA2P_REQUIRE((out_dtype == IA2P_BF16 || out_dtype == IA2P_F32) && (residual == nullptr || res_dtype == IA2P_BF16 || res_dtype == IA2P_F32),
                IA2P_E_ARG, "conv3x3: out/residual dtype must be bf16 or f32");
@@ -1083,7 +1083,9 @@ extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64
       koff += cs[s];
     }
   } else {
-    // x = 2*xo + px: one decimated view per parity (py, px); tap k in {0,1,2} reads parity (k==1 ? 0 : 1) at offset (k==0 ? -1 : 0)
+    // x = 2*xo + px: one decimated view per parity (py, px).  pad 1 (UNet Downsample2D): input index 2*xo + k - 1, so tap k in
+    // {0,1,2} reads parity (k==1 ? 0 : 1) at offset (k==0 ? -1 : 0).  pad_end (VAE encoder Downsample2D: padding 0 after
+    // F.pad(0,1,0,1)): input index 2*xo + k, so tap k reads parity (k & 1) at offset (k==2 ? +1 : 0).
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
@@ -1092,9 +1094,9 @@ extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64
       }
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
-        const int py = ky == 1 ? 0 : 1, px = kx == 1 ? 0 : 1;
-        p.taps[nt++] = TapEntry{(int16_t)(py * 2 + px), (int16_t)(kx == 0 ? -1 : 0), (int16_t)(ky == 0 ? -1 : 0),
-                                (int16_t)(Cin / 64), (int32_t)((ky * 3 + kx) * Cin)};
+        const int py = pad_end ? (ky & 1) : (ky == 1 ? 0 : 1), px = pad_end ? (kx & 1) : (kx == 1 ? 0 : 1);
+        const int ox = pad_end ? (kx == 2 ? 1 : 0) : (kx == 0 ? -1 : 0), oy = pad_end ? (ky == 2 ? 1 : 0) : (ky == 0 ? -1 : 0);
+        p.taps[nt++] = TapEntry{(int16_t)(py * 2 + px), (int16_t)ox, (int16_t)oy, (int16_t)(Cin / 64), (int32_t)((ky * 3 + kx) * Cin)};
       }
   }
   p.ntaps = nt;
@@ -1112,4 +1114,18 @@ extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64
   p.ldo = Cout; p.ldr = Cout; p.geglu = 0;
   p.out_f32 = out_dtype == IA2P_F32; p.res_f32 = res_dtype == IA2P_F32;
   return dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int stride,
+                                      const void* w, const void* sc_a, int64_t sc_ca, const void* sc_b, int64_t sc_cb,
+                                      void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
+                                      const void* residual, int res_dtype, void* stream) {
+  return conv3x3_impl(x, B, H, W, Cin, stride, false, w, sc_a, sc_ca, sc_b, sc_cb, out, out_dtype, Cout, bias, rowbias, residual,
+                      res_dtype, stream);
+}
+
+extern "C" int ia2p_conv3x3_s2_padend_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w,
+                                                void* out, int out_dtype, int64_t Cout, const float* bias, void* stream) {
+  return conv3x3_impl(x, B, H, W, Cin, 2, true, w, nullptr, 0, nullptr, 0, out, out_dtype, Cout, bias, nullptr, nullptr, IA2P_BF16,
+                      stream);
 }

@@ -103,6 +103,22 @@ def axpby(eps, x, c_x, c_e, out=None):
     return out
 
 
+def polar_interpolate(x, y, alpha, out=None):
+    """``InstructAny2PixPipeline.polar_intrtpolate`` (pipeline.py:295-300): blend two latents and restore the blended norm;
+    norms are taken over the whole tensor, fp32."""
+    lib = _lib.load()
+    x, y = _f32(x, "x").contiguous(), _f32(y, "y").contiguous()
+    assert x.shape == y.shape
+    if out is None:
+        out = torch.empty_like(x)
+    ws = torch.empty(int(lib.ia2p_polar_workspace_bytes()), device=x.device, dtype=torch.uint8)
+    global LAUNCHES
+    LAUNCHES += 1                                                # two kernels per call
+    _run(lib.ia2p_polar_interpolate, (x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(), float(alpha), ws.data_ptr(),
+                                          _stream()), "polar_interpolate")
+    return out
+
+
 def prior_cfg_ddpm_step(x0_pair, x, noise, sqrt_a, sqrt_1ma, g, c_x0, c_x, sigma, out=None):
     lib = _lib.load()
     x0_pair, x = _f32(x0_pair, "x0_pair"), _f32(x, "x")
@@ -299,6 +315,35 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
     return out
 
 
+def conv3x3_down_padend(x, w, cout, bias=None, out_dtype=torch.bfloat16):
+    """stride-2 3x3 conv padded at the bottom/right only (VAE encoder Downsample2D); x NHWC bf16, w [cout, 9*Cin] bf16."""
+    lib = _lib.load()
+    _need(x, torch.bfloat16, "x", 4)
+    _need(w, torch.bfloat16, "w", 2)
+    x = x.contiguous()
+    B, H, W, Cin = x.shape
+    assert w.is_contiguous() and w.shape == (cout, 9 * Cin) and H % 2 == 0 and W % 2 == 0
+    out = torch.empty(B, H // 2, W // 2, cout, device=x.device, dtype=out_dtype)
+    bias = _f32(bias, "bias")
+    global _FLOPS
+    _FLOPS = 2.0 * B * (H // 2) * (W // 2) * cout * w.shape[1]
+    _run(lib.ia2p_conv3x3_s2_padend_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, w.data_ptr(), out.data_ptr(), _DT[out_dtype], cout,
+                                                    _ptr(bias), _stream()), "conv3x3_down_padend")
+    return out
+
+
+def gaussian_sample(moments, noise, scale=1.0):
+    """scale * (mean + exp(0.5 clamp(logvar)) * noise) from moments (B, 2C, H, W) fp32; noise None -> scale * mean."""
+    lib = _lib.load()
+    moments = _f32(moments, "moments").contiguous()
+    B, C2, H, W = moments.shape
+    noise = None if noise is None else _f32(noise, "noise").contiguous()
+    out = torch.empty(B, C2 // 2, H, W, device=moments.device, dtype=torch.float32)
+    _run(lib.ia2p_gaussian_sample, (moments.data_ptr(), _ptr(noise), out.data_ptr(), B, C2 // 2, H * W, float(scale), _stream()),
+         "gaussian_sample")
+    return out
+
+
 def conv_in(x_nchw, w, bias, out_batch=None, out_dtype=torch.bfloat16):
     """conv_in from NCHW latents to NHWC (bf16|fp32); batch read modulo x.shape[0] (CFG duplication)."""
     lib = _lib.load()
@@ -329,7 +374,33 @@ def conv_out(x, w, bias, out_dtype=torch.float32):
     return out
 
 
+def conv1x1_nchw_small(x, w, bias, scale=1.0):
+    """1x1 conv over <= 8 channels, NCHW fp32 -> NCHW fp32: scale * (w x) + bias (VAE post_quant_conv / quant_conv)."""
+    lib = _lib.load()
+    x = _f32(x, "x").contiguous()
+    B, cin, H, W = x.shape
+    w, bias = _f32(w, "w").reshape(-1, cin).contiguous(), _f32(bias, "bias")
+    cout = w.shape[0]
+    out = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
+    _run(lib.ia2p_conv1x1_nchw_small, (x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), B, cin, cout, H * W, float(scale),
+                                           _stream()), "conv1x1_nchw_small")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ attention
+def softmax_rows(scores, scale, out=None):
+    """softmax(scale * scores) over the last dim of an fp32 matrix -> bf16."""
+    lib = _lib.load()
+    _need(scores, torch.float32, "scores", 2)
+    rows, cols = scores.shape
+    assert scores.stride(1) == 1
+    if out is None:
+        out = torch.empty(rows, cols, device=scores.device, dtype=torch.bfloat16)
+    _run(lib.ia2p_softmax_rows_f32_bf16, (scores.data_ptr(), scores.stride(0), out.data_ptr(), out.stride(0), rows, cols,
+                                              float(scale), _stream()), "softmax_rows")
+    return out
+
+
 def flash_self_attn(qkv, batch, n_tokens, heads, out=None):
     """qkv: [batch*n_tokens, 3*C] bf16 (q | k | v); returns [batch*n_tokens, C]."""
     lib = _lib.load()

@@ -68,6 +68,17 @@ class B200Sampler:
             ent["kv_i"].copy_(kv[1])
         return ent, table, kv[2], kv[3]
 
+    # ------------------------------------------------------------------ start latent (pipeline.py:330-336)
+    @torch.no_grad()
+    def start_latent(self, latent_inv, alpha=0.7, noise=None, generator=None):
+        """``polar_intrtpolate(latent_inv, randn_like(latent_inv), alpha)`` (pipeline.py:295-300, :332-336): the inverted
+        latent is blended with fresh noise and the blend is rescaled to the blended norm.  ``noise`` may be supplied (parity
+        tests); otherwise it is drawn like the reference does (global RNG or ``generator``)."""
+        x = latent_inv.to(self.unet.device, torch.float32)
+        if noise is None:
+            noise = torch.randn(x.shape, device=x.device, dtype=torch.float32, generator=generator)
+        return ops.polar_interpolate(x, noise.to(x.device, torch.float32), alpha)
+
     # ------------------------------------------------------------------ generation (CFG, DDIM eta=0)
     @torch.no_grad()
     def generate(self, latents, ctx, added_cond_kwargs, num_inference_steps=50, guidance_scale=10.0, trace=None,

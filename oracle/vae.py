@@ -92,6 +92,72 @@ class OracleVAEDecoder(nn.Module):
         return self.conv_out(F.silu(self.conv_norm_out(x)))
 
 
+class _Down(nn.Module):
+    def __init__(self, cin, cout, n, groups, add_down):
+        super().__init__()
+        self.resnets = nn.ModuleList([_Res(cin if i == 0 else cout, cout, groups) for i in range(n)])
+        if add_down:
+            # [3P] Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) then a stride-2 3x3 conv without padding
+            self.downsamplers = nn.ModuleList([nn.ModuleDict(dict(conv=nn.Conv2d(cout, cout, 3, stride=2, padding=0)))])
+        self.add_down = add_down
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.add_down:
+            x = self.downsamplers[0]["conv"](F.pad(x, (0, 1, 0, 1)))
+        return x
+
+
+class OracleVAEEncoder(nn.Module):
+    """Restated diffusers==0.26.3 ``AutoencoderKL`` ENCODER + ``quant_conv`` + ``DiagonalGaussianDistribution`` (SDXL VAE
+    config): the path ``prepare_latents`` of the inversion pipeline takes (ddim/pnp_pipeline.py:195-204:
+    ``vae.encode(image).latent_dist.sample(generator) * vae.config.scaling_factor``).  Parity unpinned (third-party module)."""
+
+    def __init__(self, cfg=None, in_channels=3):
+        super().__init__()
+        cfg = dict(SDXL_VAE if cfg is None else cfg)
+        self.cfg = cfg
+        ch, G = cfg["block_out_channels"], cfg["norm_num_groups"]
+        self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
+        downs, prev = [], ch[0]
+        for i, c in enumerate(ch):
+            downs.append(_Down(prev, c, cfg["layers_per_block"], G, add_down=i < len(ch) - 1))
+            prev = c
+        self.down_blocks = nn.ModuleList(downs)
+        self.mid_res0, self.mid_attn, self.mid_res1 = _Res(ch[-1], ch[-1], G), _Attn(ch[-1], G), _Res(ch[-1], ch[-1], G)
+        self.conv_norm_out = nn.GroupNorm(G, ch[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[-1], 2 * cfg["latent_channels"], 3, padding=1)
+        self.quant_conv = nn.Conv2d(2 * cfg["latent_channels"], 2 * cfg["latent_channels"], 1)
+
+    @torch.no_grad()
+    def moments(self, images):
+        x = self.conv_in(images.float())
+        for d in self.down_blocks:
+            x = d(x)
+        x = self.mid_res1(self.mid_attn(self.mid_res0(x)))
+        return self.quant_conv(self.conv_out(F.silu(self.conv_norm_out(x))))
+
+    @torch.no_grad()
+    def encode(self, images, noise=None):
+        """images (B,3,H,W) in [-1,1] -> latents (B,4,H/8,W/8) = sample * scaling_factor (noise None: the mode)."""
+        mean, logvar = self.moments(images).chunk(2, dim=1)
+        z = mean if noise is None else mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise
+        return z * self.cfg["scaling_factor"]
+
+
+def to_diffusers_keys(sd, side):
+    """state dict of an Oracle VAE half -> the diffusers AutoencoderKL key names ``B200VAE`` uses."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith(("post_quant_conv", "quant_conv")):
+            out[k] = v
+            continue
+        k = k.replace("mid_res0", "mid_block.resnets.0").replace("mid_res1", "mid_block.resnets.1").replace("mid_attn", "mid_block.attentions.0")
+        out[f"{side}.{k}"] = v
+    return out
+
+
 def psnr(a, b, data_range=2.0):
     """PSNR in dB between two image batches in [-1, 1] (data_range 2), computed over the whole batch."""
     mse = ((a.float() - b.float()) ** 2).mean().clamp_min(1e-20)

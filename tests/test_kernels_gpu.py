@@ -136,6 +136,25 @@ def test_gemm_geglu(M, C):
     assert rel(out, ref) < TOL
 
 
+def test_polar_interpolate_matches_reference_golden():
+    """pipeline.py:295-300 run by oracle/gen_golden.py on the reference's own function (tests/golden/scalar_fns.npz), plus a
+    full-size latent against the same formula in fp64."""
+    import os
+    import numpy as np
+    from oracle.synth import synth_input
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "scalar_fns.npz"))
+    x, y = synth_input("bd/x", (1, 4, 8, 8)), synth_input("polar/y", (1, 4, 8, 8))
+    out = ops.polar_interpolate(x.to(DEV), y.to(DEV), 0.7)
+    np.testing.assert_allclose(out.cpu().numpy(), gold["polar"], rtol=2e-6, atol=2e-6)
+    x, y = rnd(1, 4, 128, 128, dtype=torch.float32, seed=5), rnd(1, 4, 128, 128, dtype=torch.float32, seed=6)
+    out = ops.polar_interpolate(x, y, 0.3)
+    xd, yd = x.double(), y.double()
+    ll = xd * 0.3 + yd * 0.7
+    ref = ll / ll.norm() * (xd.norm() * 0.3 + yd.norm() * 0.7)
+    assert rel(out, ref) < 1e-6
+    assert torch.equal(out, ops.polar_interpolate(x, y, 0.3))        # bit-reproducible (no atomics)
+
+
 def test_gelu_accuracy():
     """the epilogue's exact-GELU evaluation (A&S 7.1.26) against torch's erf GELU in fp64, through a GEGLU GEMM whose value
     half is the constant 1 and whose gate half sweeps [-10, 10]: |error| must stay below bf16 output rounding (2^-9 rel)."""

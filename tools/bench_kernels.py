@@ -62,6 +62,23 @@ def bench_mainloop():
     print(f"cuBLAS square 8192: {ms * 1e3:8.1f} us  {2.0 * 8192 ** 3 / ms / 1e9:7.1f} TFLOP/s")
 
 
+def bench_vae():
+    """SDXL VAE at 1024^2 (random init): decode of B latents, encode of B images; FLOPs counted analytically from the convs/linears"""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    vae = bench.build_vae(torch.device("cuda", 0))
+    for B in (1, 4):
+        lat = torch.randn(B, 4, 128, 128, device=dev)
+        ops.PROFILE = []
+        vae.decode(lat)
+        torch.cuda.synchronize()
+        rec, ops.PROFILE = ops.PROFILE, None
+        flops = sum(r[1] for r in rec)
+        ms = timeit(lambda i: vae.decode(lat), iters=5, warm=2)
+        print(f"vae decode 1024^2 B={B}: {ms:7.2f} ms  {flops / ms / 1e9:7.1f} TFLOP/s (tensor-core FLOPs {flops / 1e12:.2f} T)  "
+              f"peak mem {torch.cuda.max_memory_allocated() / 2 ** 30:.1f} GiB")
+
+
 def bench_lnfold():
     """consumer GEMMs with and without the LayerNorm fold, producer GEMM with and without the LN outputs."""
     M, C = 8192, 1280
@@ -120,6 +137,6 @@ def bench_norm():
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.manual_seed(0)
-    for k, fn in (("gemm", bench_gemm), ("conv", bench_conv), ("attn", bench_attn), ("norm", bench_norm), ("lnfold", bench_lnfold), ("mainloop", bench_mainloop)):
+    for k, fn in (("gemm", bench_gemm), ("conv", bench_conv), ("attn", bench_attn), ("norm", bench_norm), ("lnfold", bench_lnfold), ("mainloop", bench_mainloop), ("vae", bench_vae)):
         if which in (k, "all"):
             fn()
