@@ -48,13 +48,11 @@ def peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes (read + write) per tc_gemm_kernel launch, averaged over the launches of one UNet forward, from the committed
-    `ncu --set full` capture (profiles/gemm_traffic_r01.json; not measured live -- a run under ncu is never a bench value)."""
+    """DRAM bytes (read + write) per tc_gemm_kernel launch, averaged over the 480 launches of one UNet step, from the committed
+    ncu capture (profiles/gemm_traffic_r01.json; not measured live -- a run under ncu is never a bench value)."""
     p = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return dict(dram_bytes_per_launch=d["dram_bytes_per_launch"], algorithmic_bytes_per_launch=d.get("algorithmic_bytes_per_launch"),
-                    launches=d["launches"], source="profiles/gemm_traffic_r01.json")
+        return json.load(open(p))["dram_bytes_per_launch"]
     return None
 
 
@@ -192,11 +190,12 @@ def profile_dominant_kernel(unet, sampler, dev_in, B):
     torch.cuda.synchronize()
     rec, ops.PROFILE = ops.PROFILE, None
     by, shapes = {}, {}
-    for name, flops, e0, e1, tag in rec:
+    for name, flops, e0, e1, tag, nbytes in rec:
         ms = e0.elapsed_time(e1)
-        d = by.setdefault(name, dict(ms=0.0, flops=0.0, n=0))
+        d = by.setdefault(name, dict(ms=0.0, flops=0.0, n=0, bytes=0.0))
         d["ms"] += ms
         d["flops"] += flops
+        d["bytes"] += nbytes
         d["n"] += 1
         if tag:
             t = shapes.setdefault(tag, dict(ms=0.0, flops=0.0, n=0))
@@ -367,7 +366,7 @@ def main():
     by = profile_dominant_kernel(unet, sampler, dev_in, B)
     n_forward_kernels = sum(d["n"] + (d["n"] if k == "ia2p_groupnorm_nhwc" else 0) for k, d in by.items())
     gpu_launches = launches_eager + (0 if args.no_graph else args.steps * NS * n_forward_kernels)
-    tc = dict(ms=0.0, flops=0.0, n=0)
+    tc = dict(ms=0.0, flops=0.0, n=0, bytes=0.0)
     for k in ("ia2p_gemm_bf16", "ia2p_gemm_ln_bf16", "ia2p_conv3x3_nhwc_bf16"):
         if k in by:
             for f in tc:
@@ -376,6 +375,7 @@ def main():
     ach = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] else 0.0
     roof = dict(kernel="tc_gemm_kernel (tcgen05 implicit GEMM: linears + 3x3 convs)", bound="tensor", achieved=ach,
                 peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"], traffic=ncu_traffic(), peak_source=pk["src"] + " bf16_tflops_sustained",
+                algorithmic_bytes_per_launch=tc["bytes"] / max(tc["n"], 1), algorithmic_flops_per_launch=tc["flops"] / max(tc["n"], 1),
                 launches_per_forward=tc["n"], avg_launch_ms=tc["ms"] / max(tc["n"], 1), share_of_forward=tc["ms"] / total_ms if total_ms else None,
                 forward_breakdown_ms={k: round(d["ms"], 3) for k, d in sorted(by.items(), key=lambda kv: -kv[1]["ms"])})
     out = dict(metric="images/sec 1024^2 50-step DDIM CFG" if L == 128 else "images/sec 512^2 50-step DDIM CFG",

@@ -25,11 +25,12 @@ PROFILE = None
 TAG_ALWAYS = False          # tools/timeline_step.py: build the shape tags without event profiling
 _KERNELS_PER_CALL = {"ia2p_groupnorm_nhwc": 2}
 _FLOPS = 0.0
+_BYTES = 0.0                # algorithmic bytes of the call (operands read once + results written once), for bench.py's roofline
 _TAG = ""
 
 
 def _run(fn, args, what):
-    global LAUNCHES, _FLOPS, _TAG
+    global LAUNCHES, _FLOPS, _TAG, _BYTES
     LAUNCHES += _KERNELS_PER_CALL.get(fn.__name__, 1)
     prof = PROFILE
     if prof is not None:
@@ -37,10 +38,11 @@ def _run(fn, args, what):
         e0.record()
         status = fn(*args)
         e1.record()
-        prof.append((fn.__name__, _FLOPS, e0, e1, _TAG))
+        prof.append((fn.__name__, _FLOPS, e0, e1, _TAG, _BYTES))
     else:
         status = fn(*args)
     _FLOPS = 0.0
+    _BYTES = 0.0
     _TAG = ""
     if status != 0:
         _lib.check(status, what)
@@ -264,8 +266,10 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
         ln_stats, ln_c1 = _f32(ln_stats, "ln_stats"), _f32(ln_c1, "ln_c1")
         assert ln_stats.shape[0] == M and ln_c1.numel() == N
         ln_parts = ln_stats.shape[1]
-    global _FLOPS, _TAG
+    global _FLOPS, _TAG, _BYTES
     _FLOPS = 2.0 * M * N * (K1 + K2)
+    _BYTES = (2.0 * M * (K1 + K2) + 2.0 * N * (K1 + K2) + M * n_out * out.element_size()
+              + (M * n_out * residual.element_size() if residual is not None else 0) + (M * N * 2 + M * 8 * 4 if want_ln else 0))
     if PROFILE is not None or TAG_ALWAYS:
         _TAG = (f"gemm M{M} N{N} K{K1 + K2}{' geglu' if geglu else ''}{' res' + str(residual.dtype)[6:] if residual is not None else ''}"
                 f" out{str(out.dtype)[6:]}{' +ln_stats' if want_ln else ''}{' ln_fold' if ln is not None else ''}")
@@ -305,8 +309,10 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
         assert residual.shape == out.shape and residual.dtype in (torch.bfloat16, torch.float32)
         res_dt = _DT[residual.dtype]
     bias, rowbias = _f32(bias, "bias"), _f32(rowbias, "rowbias")
-    global _FLOPS, _TAG
+    global _FLOPS, _TAG, _BYTES
     _FLOPS = 2.0 * B * Ho * Wo * cout * w.shape[1]
+    _BYTES = (2.0 * B * H * W * (Cin + ca + cb) + 2.0 * w.numel() + B * Ho * Wo * cout * out.element_size()
+              + (residual.numel() * residual.element_size() if residual is not None else 0))
     if PROFILE is not None or TAG_ALWAYS:
         _TAG = f"conv {H}x{W} C{Cin}->{cout} K{w.shape[1]} s{stride}{' res' if residual is not None else ''} out{str(out_dtype)[6:]}"
     _run(lib.ia2p_conv3x3_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, stride, w.data_ptr(), _ptr(sc_a), ca, _ptr(sc_b), cb,
