@@ -364,13 +364,13 @@ def main():
     # launches: graph replays re-issue the captured kernels
     per_forward = getattr(sampler, "launches_per_forward", None)
     by = profile_dominant_kernel(unet, sampler, dev_in, B)
-    n_forward_kernels = sum(d["n"] + (d["n"] if k == "ia2p_groupnorm_nhwc" else 0) for k, d in by.items())
+    n_forward_kernels = sum(d["n"] * ops._KERNELS_PER_CALL.get(k, 1) for k, d in by.items())
     gpu_launches = launches_eager + (0 if args.no_graph else args.steps * NS * n_forward_kernels)
     tc = dict(ms=0.0, flops=0.0, n=0, bytes=0.0)
-    for k in ("ia2p_gemm_bf16", "ia2p_gemm_ln_bf16", "ia2p_conv3x3_nhwc_bf16"):
+    for k in ("ia2p_gemm_bf16", "ia2p_gemm_ln_bf16", "ia2p_conv3x3_nhwc_bf16", "ia2p_conv_up2x_nhwc_bf16"):
         if k in by:
             for f in tc:
-                tc[f] += by[k][f]
+                tc[f] += by[k][f] * (ops._KERNELS_PER_CALL.get(k, 1) if f == "n" else 1)
     total_ms = sum(d["ms"] for d in by.values())
     ach = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] else 0.0
     roof = dict(kernel="tc_gemm_kernel (tcgen05 implicit GEMM: linears + 3x3 convs)", bound="tensor", achieved=ach,

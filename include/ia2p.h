@@ -137,6 +137,12 @@ int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64
                            void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
                            const void* residual, int res_dtype, void* stream);
 
+/* Nearest-2x upsample + 3x3 pad-1 conv in one op ([3P] Upsample2D = F.interpolate(scale_factor=2, "nearest") -> conv; UNet up
+ * blocks, VAE decoder): four 2x2 convs over the LOW-resolution map, one per output parity, with pre-summed weights
+ * w4 [4][Cout][4*Cin] bf16 (instructany2pix_b200.packing.pack_conv3x3_up2x).  x [B,H,W,Cin] bf16 -> out [B,2H,2W,Cout] fp32. */
+int ia2p_conv_up2x_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w4, void* out,
+                             int64_t Cout, const float* bias, void* stream);
+
 /* Stride-2 3x3 conv with padding only at the bottom / right (input index 2*o + k): the VAE encoder's Downsample2D
  * ([3P] diffusers: padding=0 after F.pad(x, (0,1,0,1)); reached from vae.encode at ddim/pnp_pipeline.py:195-204). */
 int ia2p_conv3x3_s2_padend_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w,

@@ -50,6 +50,7 @@ struct TcParams {
   const void* residual;            // bf16 or fp32 (res_f32)
   void* out;                       // bf16 or fp32 (out_f32)
   long long ldo, ldr;
+  long long ost_x, ost_y, ost_b;   // EPI >= 1 output map: element strides of the pixel grid (0 -> dense: ldo, ldo*Wo, ldo*Wo*Ho)
   int geglu, out_f32, res_f32;
   // LayerNorm folding: a PRODUCER of the fp32 residual stream also emits a bf16 copy of its output rows and
   // per-row partial (sum, sum of squares) over each column half of every N tile; a CONSUMER multiplies the raw bf16 rows
@@ -897,7 +898,8 @@ static int dispatch_tc(TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
     const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TB = 128 >> (p.tw_log2 + p.th_log2);
     const uint32_t box[4] = {16, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
     const uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
-    const uint64_t str[4] = {1, (uint64_t)p.ldo, (uint64_t)p.ldo * p.Wo, (uint64_t)p.ldo * p.Wo * p.Ho};
+    const uint64_t str[4] = {1, (uint64_t)(p.ost_x ? p.ost_x : p.ldo), (uint64_t)(p.ost_y ? p.ost_y : p.ldo * p.Wo),
+                             (uint64_t)(p.ost_b ? p.ost_b : p.ldo * p.Wo * p.Ho)};
     if (int e = make_map(&maps.o, p.out, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     maps.o2 = maps.o;
     if (p.out2 != nullptr) {
@@ -1128,4 +1130,56 @@ extern "C" int ia2p_conv3x3_s2_padend_nhwc_bf16(const void* x, int64_t B, int64_
                                                 void* out, int out_dtype, int64_t Cout, const float* bias, void* stream) {
   return conv3x3_impl(x, B, H, W, Cin, 2, true, w, nullptr, 0, nullptr, 0, out, out_dtype, Cout, bias, nullptr, nullptr, IA2P_BF16,
                       stream);
+}
+
+// Nearest-2x upsample folded into the following 3x3 conv ([3P] Upsample2D: F.interpolate(x, scale 2, "nearest") -> conv).  An output
+// pixel of parity (py, px) only ever sees a 2x2 neighbourhood of the LOW-resolution map (up[i] = in[i >> 1]), so the conv
+// splits into four 2x2 convs over the low-res input with pre-summed weights: 4/9 of the MACs, no upsampled tensor in HBM.
+// w4: [4 parities (py*2+px)][Cout][4*Cin] bf16, tap order (row tap, col tap); out: [B, 2H, 2W, Cout] fp32 (TMA-store epilogue
+// with a stride-2 output map per parity).
+extern "C" int ia2p_conv_up2x_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w4, void* out,
+                                        int64_t Cout, const float* bias, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && w4 && out && B > 0 && H > 0 && W > 0, IA2P_E_ARG, "conv_up2x: null pointer or empty shape");
+  IA2P_REQUIRE(Cin % 64 == 0 && Cout % 32 == 0, IA2P_E_SHAPE, "conv_up2x: Cin %% 64 == 0 and Cout %% 32 == 0 required");
+  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(out) & 31) == 0, IA2P_E_ALIGN, "conv_up2x: out must be 32-byte aligned");
+  int TW = 1; while (TW < 128 && W % (TW * 2) == 0) TW *= 2;
+  int TH = 1; while (TW * TH < 128 && H % (TH * 2) == 0) TH *= 2;
+  const int TB = 128 / (TW * TH);
+  const int64_t Ktot = 4 * Cin;
+  const int bn = pick_block_n(Cout, false);
+  const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(w4);
+  for (int par = 0; par < 4; ++par) {
+    const int py = par >> 1, px = par & 1;
+    TcMaps maps;
+    TcParams p{};
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)(W * Cin), (uint64_t)(H * W * Cin)};
+    if (int e = make_map(&maps.a[0], xb, 4, dims, str, box)) return e;
+    maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
+    int nt = 0;
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j)
+        p.taps[nt++] = TapEntry{0, (int16_t)(px == 0 ? j - 1 : j), (int16_t)(py == 0 ? i - 1 : i), (int16_t)(Cin / 64),
+                                (int32_t)((i * 2 + j) * Cin)};
+    p.ntaps = nt;
+    p.num_kb = (int)(Ktot / 64);
+    p.tw_log2 = ilog2_exact(TW); p.th_log2 = ilog2_exact(TH);
+    p.tiles_x = (int)(W / TW); p.tiles_y = (int)(H / TH);
+    p.m_tiles = p.tiles_x * p.tiles_y * (int)((B + TB - 1) / TB);
+    if (int e = make_w_map(maps, wb + (size_t)par * Cout * Ktot, Cout, Ktot, bn, p.m_tiles)) return e;
+    p.Wo = (int)W; p.Ho = (int)H; p.B = (int)B;
+    p.N = (int)Cout;
+    p.rows_per_batch = (int)(H * W);
+    p.bias = bias;
+    p.out = static_cast<float*>(out) + ((int64_t)py * 2 * W + px) * Cout;
+    p.ldo = Cout; p.ldr = Cout;
+    p.ost_x = 2 * Cout; p.ost_y = 4 * W * Cout; p.ost_b = 4 * H * W * Cout;
+    p.out_f32 = 1; p.res_f32 = 0; p.geglu = 0;
+    IA2P_REQUIRE(tma_epilogue(p), IA2P_E_ARG, "conv_up2x needs the TMA-store epilogue (IA2P_GEMM_EPI=0 is set)");
+    if (int e = dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream))) return e;
+  }
+  return 0;
 }

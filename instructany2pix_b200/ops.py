@@ -23,7 +23,7 @@ def _stream():
 LAUNCHES = 0
 PROFILE = None
 TAG_ALWAYS = False          # tools/timeline_step.py: build the shape tags without event profiling
-_KERNELS_PER_CALL = {"ia2p_groupnorm_nhwc": 2}
+_KERNELS_PER_CALL = {"ia2p_groupnorm_nhwc": 2, "ia2p_conv_up2x_nhwc_bf16": 4, "ia2p_polar_interpolate": 2}
 _FLOPS = 0.0
 _BYTES = 0.0                # algorithmic bytes of the call (operands read once + results written once), for bench.py's roofline
 _TAG = ""
@@ -114,8 +114,6 @@ def polar_interpolate(x, y, alpha, out=None):
     if out is None:
         out = torch.empty_like(x)
     ws = torch.empty(int(lib.ia2p_polar_workspace_bytes()), device=x.device, dtype=torch.uint8)
-    global LAUNCHES
-    LAUNCHES += 1                                                # two kernels per call
     _run(lib.ia2p_polar_interpolate, (x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(), float(alpha), ws.data_ptr(),
                                           _stream()), "polar_interpolate")
     return out
@@ -318,6 +316,27 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
     _run(lib.ia2p_conv3x3_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, stride, w.data_ptr(), _ptr(sc_a), ca, _ptr(sc_b), cb,
                                           out.data_ptr(), _DT[out_dtype], cout, _ptr(bias), _ptr(rowbias), _ptr(residual),
                                           res_dt, _stream()), "conv3x3")
+    return out
+
+
+def conv_up2x(x, w4, cout, bias=None):
+    """nearest-2x upsample + 3x3 conv as four parity 2x2 convs over the low-res map; x NHWC bf16, w4 [4, cout, 4*Cin] bf16
+    (packing.pack_conv3x3_up2x) -> [B, 2H, 2W, cout] fp32."""
+    lib = _lib.load()
+    _need(x, torch.bfloat16, "x", 4)
+    _need(w4, torch.bfloat16, "w4", 3)
+    x = x.contiguous()
+    B, H, W, Cin = x.shape
+    assert w4.is_contiguous() and w4.shape == (4, cout, 4 * Cin)
+    out = torch.empty(B, 2 * H, 2 * W, cout, device=x.device, dtype=torch.float32)
+    bias = _f32(bias, "bias")
+    global _FLOPS, _TAG, _BYTES
+    _FLOPS = 2.0 * B * 4 * H * W * cout * 9 * Cin                  # ALGORITHMIC flops of the 3x3 conv on the upsampled map
+    _BYTES = 2.0 * B * H * W * Cin + 2.0 * w4.numel() + 4.0 * out.numel()
+    if PROFILE is not None or TAG_ALWAYS:
+        _TAG = f"conv_up2x {H}x{W}->{2 * H}x{2 * W} C{Cin}->{cout} (4 x K{4 * Cin})"
+    _run(lib.ia2p_conv_up2x_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, w4.data_ptr(), out.data_ptr(), cout, _ptr(bias), _stream()),
+         "conv_up2x")
     return out
 
 

@@ -17,6 +17,29 @@ def pack_conv3x3(w, w_shortcut=None, dtype=torch.bfloat16):
     return p.to(dtype).contiguous()
 
 
+def pack_conv3x3_up2x(w, dtype=torch.bfloat16):
+    """Conv2d weight [Cout,Cin,3,3] of a conv that follows a nearest-2x upsample -> [4, Cout, 4*Cin]: for output parity
+    (py, px) the 3x3 taps collapse onto a 2x2 neighbourhood of the low-resolution map (rows {y-1, y} for py = 0, {y, y+1} for
+    py = 1; same for columns), with the weights of coinciding taps summed in fp32.  Tap order (row tap, col tap), channels inner:
+    the layout ia2p_conv_up2x_nhwc_bf16 expects."""
+    cout, cin = w.shape[:2]
+    wf = w.detach().float()
+    sets = {0: ([0], [1, 2]), 1: ([0, 1], [2])}            # parity -> source kernel indices of (first tap, second tap)
+    out = []
+    for py in range(2):
+        for px in range(2):
+            taps = []
+            for i in range(2):
+                for j in range(2):
+                    acc = torch.zeros(cout, cin, device=w.device)
+                    for ky in sets[py][i]:
+                        for kx in sets[px][j]:
+                            acc = acc + wf[:, :, ky, kx]
+                    taps.append(acc)
+            out.append(torch.cat(taps, dim=1))
+    return torch.stack(out, 0).to(dtype).contiguous()
+
+
 def interleave_geglu(w, b=None, group=32):
     """GEGLU proj weight [8C, C] (rows [0,4C) value | [4C,8C) gate) -> rows interleaved in `group`-row
     blocks [value_0 | gate_0 | value_1 | gate_1 ...] so value/gate of one output land in the same accumulator tile."""

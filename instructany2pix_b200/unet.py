@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from . import ops
 from .attention_processor import B200AttnProcessor, B200IPAttnProcessor, is_ip_processor, is_plain_processor
-from .packing import interleave_geglu, pack_conv3x3
+from .packing import interleave_geglu, pack_conv3x3, pack_conv3x3_up2x
 
 
 @dataclass
@@ -169,6 +169,7 @@ class B200UNet(nn.Module):
         # LayerNorm folded into the consuming GEMM's epilogue (no separate normalisation pass); False restores the
         # standalone ia2p_layernorm kernels (A/B measurements, or nets whose token means dwarf their spread)
         self.fuse_ln = True
+        self.fold_upsample = True     # Upsample2D as four parity 2x2 convs over the low-res map (4/9 of the MACs)
         if config is None:
             config = B200UNetConfig(**config_overrides)
         elif not isinstance(config, B200UNetConfig):
@@ -352,6 +353,8 @@ class B200UNet(nn.Module):
                     wg=bf(wg), bg=f32(bg), wf=bf(m.ff.net[2].weight), bf=f32(m.ff.net[2].bias))
             elif isinstance(m, _Sampler):
                 P[name] = dict(w=pack_conv3x3(m.conv.weight), b=f32(m.conv.bias))
+                if ".upsamplers." in name:       # nearest-2x upsample folded into the conv: four parity 2x2 convs
+                    P[name]["w4"] = pack_conv3x3_up2x(m.conv.weight)
         P["conv_in"] = (f32(self.conv_in.weight), f32(self.conv_in.bias))
         P["conv_out"] = (f32(self.conv_out.weight.permute(0, 2, 3, 1)), f32(self.conv_out.bias))
         P["norm_out"] = (f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias))
@@ -591,7 +594,10 @@ class B200UNet(nn.Module):
                     x = transformer(f"up_blocks.{i}.attentions.{j}", blk.attentions[j], x)
             if hasattr(blk, "upsamplers"):
                 p = P[f"up_blocks.{i}.upsamplers.0"]
-                x = ops.conv3x3(ops.upsample2x(x), p["w"], p["w"].shape[0], bias=p["b"], out_dtype=SD)
+                if SD == torch.float32 and self.fold_upsample:
+                    x = ops.conv_up2x(ops.to_bf16(x), p["w4"], p["w"].shape[0], bias=p["b"])
+                else:
+                    x = ops.conv3x3(ops.upsample2x(x), p["w"], p["w"].shape[0], bias=p["b"], out_dtype=SD)
         g, b = P["norm_out"]
         x = ops.groupnorm(x, None, g, b, G, cfg.norm_eps, True)
         w_out, b_out = P["conv_out"]

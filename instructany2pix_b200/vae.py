@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .packing import pack_conv3x3
+from .packing import pack_conv3x3, pack_conv3x3_up2x
 
 
 @dataclass
@@ -176,6 +176,8 @@ class B200VAE(nn.Module):
                                wv=bf(m.to_v.weight), bv=f32(m.to_v.bias), wo=bf(m.to_out[0].weight), bo=f32(m.to_out[0].bias))
             elif isinstance(m, _ConvHolder):
                 P[name] = dict(w=pack_conv3x3(m.conv.weight), b=f32(m.conv.bias))
+                if ".upsamplers." in name:
+                    P[name]["w4"] = pack_conv3x3_up2x(m.conv.weight)
         for side in ("decoder", "encoder"):
             if hasattr(self, side):
                 mod = getattr(self, side)
@@ -240,7 +242,7 @@ class B200VAE(nn.Module):
                 x = self._res(P, f"decoder.up_blocks.{i}.resnets.{j}", x)
             if hasattr(blk, "upsamplers"):
                 q = P[f"decoder.up_blocks.{i}.upsamplers.0"]
-                x = ops.conv3x3(ops.upsample2x(x), q["w"], q["w"].shape[0], bias=q["b"], out_dtype=torch.float32)
+                x = ops.conv_up2x(ops.to_bf16(x), q["w4"], q["w"].shape[0], bias=q["b"])     # Upsample2D: nearest 2x + conv, folded
         h = ops.groupnorm(x, None, *P["decoder.norm_out"], G, 1e-6, True)
         return ops.conv_out(h, *P["decoder.conv_out"], out_dtype=torch.float32)
 

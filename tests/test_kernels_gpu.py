@@ -188,6 +188,20 @@ def test_conv3x3(B, H, W, Cin, Cout, stride):
     assert rel(out, _conv_ref(x, w, stride)) < TOL
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 32, 32, 128, 160), (2, 64, 64, 64, 320), (3, 8, 8, 64, 128), (1, 24, 48, 64, 64)])
+def test_conv_up2x(B, H, W, Cin, Cout):
+    """nearest-2x upsample + 3x3 conv as four parity 2x2 convs over the low-res map (pre-summed weights) vs the plain formula."""
+    from instructany2pix_b200.packing import pack_conv3x3_up2x
+    x = rnd(B, H, W, Cin)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    b = rnd(Cout, dtype=torch.float32)
+    out = ops.conv_up2x(x, pack_conv3x3_up2x(w), Cout, bias=b)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), b, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape == (B, 2 * H, 2 * W, Cout)
+    assert rel(out, ref) < 3e-3          # the summed taps are re-rounded to bf16 (2^-9 on those weights)
+
+
 def test_conv3x3_fused_shortcut_bias_temb_residual():
     from instructany2pix_b200.packing import pack_conv3x3
     B, H, W, Cin, Cout, Ca, Cb = 2, 16, 16, 128, 64, 64, 128
