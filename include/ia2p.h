@@ -112,7 +112,7 @@ int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64
 /* ia2p_gemm_bf16 + LayerNorm folding (replaces [3P] BasicTransformerBlock.norm1/2/3 followed by to_q/k/v, attn2.to_q and
  * the GEGLU projection -- SURVEY A.3 -- without a separate normalisation pass):
  *   PRODUCER (a GEMM writing the fp32 residual stream): out_bf16 (row pitch ldo2) receives a bf16 copy of the output rows and
- *     stats_out[M][ia2p_gemm_ln_parts(N)][2] the per-row partial (sum, sum of squares) of every column half-tile.
+ *     stats_out[M][ia2p_gemm_ln_parts(M, N)][2] the per-row partial (sum, sum of squares) of every column half-tile.
  *   CONSUMER: A = those raw bf16 rows, W = bf16(W_linear * gamma) (host pre-scaled), ln_c1[n] = sum_k W[n,k], bias[n] must
  *     already contain W_linear @ beta; the epilogue applies  rstd[m] * (acc - mean[m] * ln_c1[n]) + bias[n]  (before GEGLU)
  *     with mean / rstd of row m reduced, in fixed order, from ln_stats[M][ln_parts][2]; normalised width = K1 + K2.
@@ -124,7 +124,7 @@ int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, in
                       void* out_bf16, int64_t ldo2, float* stats_out,
                       const float* ln_stats, int64_t ln_parts, const float* ln_c1, float ln_eps, void* stream);
 /* number of (sum, sumsq) partials per row a producer with N output columns writes */
-int64_t ia2p_gemm_ln_parts(int64_t N);
+int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N);   /* depends on the tile width the producer picks for (M, N) */
 
 /* 3x3 conv (pad 1, stride 1|2) on NHWC bf16 as implicit GEMM, with an optional fused 1x1 shortcut conv
  * (extra K range) over up to two raw sources, bias, per-image channel bias (time embedding) and residual.

@@ -780,16 +780,24 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   return 0;
 }
 
-static int pick_block_n(int64_t N, bool geglu) {
+// Tile width: the widest of {256, 160, 128, 64} that divides N and still yields enough tiles to occupy the GPU; problems with
+// few output rows (batch-1 512^2: M = 512 -> 4 row tiles) fall through to the narrowest one, so that e.g. the FF-out GEMM
+// (N 1280, K 5120) streams its weights through 80 CTAs instead of 20.
+constexpr int kMinTilesForWideBlock = 120;
+static int pick_block_n(int64_t N, bool geglu, int64_t m_tiles) {
   if (const char* e = getenv("IA2P_GEMM_BN")) {          // experiments only
     const int v = atoi(e);
-    if ((v == 128 || v == 160 || v == 256) && N % v == 0 && (!geglu || v % 64 == 0)) return v;
+    if ((v == 64 || v == 128 || v == 160 || v == 256) && N % v == 0 && (!geglu || v % 64 == 0)) return v;
   }
-  if (geglu) return (N % 256 == 0) ? 256 : 128;
-  if (N % 256 == 0) return 256;
-  if (N % 160 == 0) return 160;
-  if (N % 128 == 0 || N > 128) return 128;
-  return 128;
+  const int cand[4] = {256, 160, 128, 64};
+  int last = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int c = cand[i];
+    if (N % c != 0 || (geglu && c % 64 != 0)) continue;
+    last = c;
+    if (m_tiles * (N / c) >= kMinTilesForWideBlock) return c;
+  }
+  return last != 0 ? last : 128;                         // 128 with a ragged last tile when nothing divides N
 }
 
 static bool tail_split_enabled() {
@@ -854,13 +862,14 @@ static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
 // power-capped full step it is worth ~1-2 %.  Tiles with a short main loop (K <= 768) stay on the single-CTA kernel: the pair
 // protocol's per-tile hand-offs (remote tmem_empty arrives, multicast commits) cost more than the B traffic saves there
 // (measured: M 32768, N 5120, K 640 GEGLU 653 -> 535 TFLOP/s with pairs).  IA2P_GEMM_CG=1 / 2 force one kernel (experiments).
-static bool use_pair(int m_tiles, int num_kb) {
+static bool use_pair(int m_tiles, int num_kb, int64_t N, int bn) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("IA2P_GEMM_CG");
     v = (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '2') ? 2 : 0;
   }
-  if (m_tiles < 2) return false;
+  if (m_tiles < 2 || bn == 64) return false;                      // BLOCK_N 64 exists for small problems only: single CTA
+  if (v == 0 && (int64_t)m_tiles * ((N + bn - 1) / bn) < 2 * sm_count()) return false;   // too few tiles to pair up
   return v == 2 || (v == 0 && num_kb > 12);
 }
 
@@ -886,7 +895,7 @@ static bool tma_residual(const TcParams& p) {
 
 template <int BN>
 static int dispatch_bn(const TcMaps& maps, TcParams& p, cudaStream_t st) {
-  const bool pair = use_pair(p.m_tiles, p.num_kb);
+  const bool pair = use_pair(p.m_tiles, p.num_kb, p.N, BN);
   if (tma_residual(p)) return pair ? launch_tc<BN, 2, 2>(maps, p, st) : launch_tc<BN, 1, 2>(maps, p, st);
   if (tma_epilogue(p)) return pair ? launch_tc<BN, 2, 1>(maps, p, st) : launch_tc<BN, 1, 1>(maps, p, st);
   return pair ? launch_tc<BN, 2, 0>(maps, p, st) : launch_tc<BN, 1, 0>(maps, p, st);
@@ -919,12 +928,16 @@ static int dispatch_tc(TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
   switch (bn) {
     case 256: return dispatch_bn<256>(maps, p, st);
     case 160: return dispatch_bn<160>(maps, p, st);
+    case 64:
+      if (tma_residual(p)) return launch_tc<64, 1, 2>(maps, p, st);
+      if (tma_epilogue(p)) return launch_tc<64, 1, 1>(maps, p, st);
+      return launch_tc<64, 1, 0>(maps, p, st);
     default: return dispatch_bn<128>(maps, p, st);
   }
 }
 
 static int make_w_map(TcMaps& maps, const void* W, int64_t N, int64_t Ktot, int bn, int m_tiles) {
-  const bool pair = use_pair(m_tiles, (int)(Ktot / 64));          // must mirror dispatch_bn: a CTA of a pair loads BN/2 rows
+  const bool pair = use_pair(m_tiles, (int)(Ktot / 64), N, bn);   // must mirror dispatch_bn: a CTA of a pair loads BN/2 rows
   const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
   const uint64_t str[2] = {1, (uint64_t)Ktot};
   const uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
@@ -964,7 +977,10 @@ extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void
                            out_dtype, epilogue, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, stream);
 }
 
-extern "C" int64_t ia2p_gemm_ln_parts(int64_t N) { return 4 * ((N + pick_block_n(N, false) - 1) / pick_block_n(N, false)); }
+extern "C" int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N) {
+  const int bn = pick_block_n(N, false, (M + 127) / 128);
+  return 4 * ((N + bn - 1) / bn);
+}
 
 extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                                  const void* W, void* out, int64_t ldo, int64_t M, int64_t N,
@@ -973,7 +989,7 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
                                  void* out_bf16, int64_t ldo2, float* stats_out,
                                  const float* ln_stats, int64_t ln_parts, const float* ln_c1, float ln_eps, void* stream) {
   if (int e = check_device()) return e;
-  IA2P_REQUIRE((ln_stats == nullptr) == (ln_c1 == nullptr) && (ln_stats == nullptr || (ln_parts > 0 && ln_parts <= 64)), IA2P_E_ARG,
+  IA2P_REQUIRE((ln_stats == nullptr) == (ln_c1 == nullptr) && (ln_stats == nullptr || (ln_parts > 0 && ln_parts <= 256)), IA2P_E_ARG,
                "gemm: ln_stats, ln_c1 and ln_parts must be given together");
   IA2P_REQUIRE((out_bf16 == nullptr && stats_out == nullptr) || epilogue != IA2P_EPI_GEGLU, IA2P_E_ARG,
                "gemm: the GEGLU epilogue cannot also produce LN statistics");
@@ -997,7 +1013,7 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
   IA2P_REQUIRE(rowbias == nullptr || rows_per_batch > 0, IA2P_E_ARG, "gemm: rowbias needs rows_per_batch");
   IA2P_REQUIRE(M < (1ll << 31) && N < (1ll << 31), IA2P_E_SHAPE, "gemm: M/N too large");
 
-  const int bn = pick_block_n(N, geglu);
+  const int bn = pick_block_n(N, geglu, (M + 127) / 128);
   TcMaps maps;
   TcParams p{};
   {
@@ -1058,7 +1074,7 @@ static int conv3x3_impl(const void* x, int64_t B, int64_t H, int64_t W, int64_t 
   int TH = 1; while (TW * TH < 128 && Ho % (TH * 2) == 0) TH *= 2;
   const int TB = 128 / (TW * TH);
   const int64_t Ktot = 9 * Cin + sc_ca + sc_cb;
-  const int bn = pick_block_n(Cout, false);
+  const int bn = pick_block_n(Cout, false, (Wo / TW) * (Ho / TH) * ((B + TB - 1) / TB));
 
   TcMaps maps;
   TcParams p{};
@@ -1147,7 +1163,7 @@ extern "C" int ia2p_conv_up2x_nhwc_bf16(const void* x, int64_t B, int64_t H, int
   int TH = 1; while (TW * TH < 128 && H % (TH * 2) == 0) TH *= 2;
   const int TB = 128 / (TW * TH);
   const int64_t Ktot = 4 * Cin;
-  const int bn = pick_block_n(Cout, false);
+  const int bn = pick_block_n(Cout, false, (W / TW) * (H / TH) * ((B + TB - 1) / TB));
   const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(w4);

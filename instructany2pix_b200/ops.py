@@ -256,7 +256,7 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
     if want_ln:
         assert not geglu
         out2 = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
-        stats = torch.empty(M, int(lib.ia2p_gemm_ln_parts(N)), 2, device=a.device, dtype=torch.float32)
+        stats = torch.empty(M, int(lib.ia2p_gemm_ln_parts(M, N)), 2, device=a.device, dtype=torch.float32)
     ln_stats = ln_c1 = None
     ln_parts, ln_eps = 0, 0.0
     if ln is not None:

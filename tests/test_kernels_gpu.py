@@ -59,6 +59,39 @@ def test_gemm_tail_split(mode):
         assert rel(ops.gemm(a, wi, bias=bi, geglu=True), h[:, :N // 2] * F.gelu(h[:, N // 2:])) < TOL
 
 
+@pytest.mark.parametrize("bn", [64, 128, 160, 256])
+@pytest.mark.parametrize("M", [384, 1000])
+def test_gemm_every_tile_width(bn, M, monkeypatch):
+    """the tile-width heuristic sends small problems to BLOCK_N 64; force each width over all epilogue variants (bf16 store,
+    TMA store, TMA residual ring + LN statistics, LN-folded consumer, GEGLU)."""
+    from instructany2pix_b200.packing import interleave_geglu
+    from instructany2pix_b200.unet import _fold_ln
+    monkeypatch.setenv("IA2P_GEMM_BN", str(bn))
+    N, K = 1280, 320
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    ref = a.float() @ w.float().t()
+    assert rel(ops.gemm(a, w), ref) < TOL
+    bias, res = rnd(N, dtype=torch.float32), rnd(M, N, dtype=torch.float32)
+    assert rel(ops.gemm(a, w, bias=bias, out_dtype=torch.float32), ref + bias) < 2e-6
+    t, tb, st = ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, want_ln=True)
+    assert rel(t, ref + bias + res) < 2e-6 and torch.equal(tb, t.to(torch.bfloat16))
+    assert rel(st.sum(1)[:, 0], t.sum(1)) < 1e-5 and rel(st.sum(1)[:, 1], (t * t).sum(1)) < 1e-5
+    ln = torch.nn.LayerNorm(N, eps=1e-5).to(DEV)
+    ln.weight.data = rnd(N, dtype=torch.float32) * 0.3 + 1.0
+    ln.bias.data = rnd(N, dtype=torch.float32) * 0.2
+    if bn != 160:                                       # GEGLU needs 64-column value|gate groups
+        w2, b2 = rnd(2560, N, scale=N ** -0.5), rnd(2560, dtype=torch.float32, scale=0.1)
+        wi, bi = interleave_geglu(w2, b2)
+        wp, c1, c2, eps = _fold_ln(wi, bi, ln)
+        out = ops.gemm(tb, wp, bias=c2, ln=(st, c1, eps), geglu=True)
+        h = F.layer_norm(t, (N,), ln.weight, ln.bias, 1e-5) @ w2.float().t() + b2
+        assert rel(out, h[:, :1280] * F.gelu(h[:, 1280:])) < 8e-3
+    w3 = rnd(640, N, scale=N ** -0.5)
+    wp, c1, c2, eps = _fold_ln(w3, None, ln)
+    out = ops.gemm(tb, wp, bias=c2, ln=(st, c1, eps))
+    assert rel(out, F.layer_norm(t, (N,), ln.weight, ln.bias, 1e-5) @ w3.float().t()) < 8e-3
+
+
 def test_gemm_epilogues():
     M, N, K = 768, 640, 320
     a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
