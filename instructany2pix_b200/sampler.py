@@ -91,11 +91,14 @@ class B200Sampler:
         B = latents.shape[0]
         assert ctx.shape[0] == 2 * B, "ctx must hold [uncond; cond] rows"
         ent, table, n_text, n_ip = self._prepare("gen", latents, ctx, added_cond_kwargs, 2 * B, s.timesteps)
-        x = ent["x"]
+        scaled_input = hasattr(s, "input_scale")           # Euler: the UNet sees x / sqrt(sigma^2 + 1), DDIM: x itself
+        x = torch.empty_like(ent["x"]) if scaled_input else ent["x"]
         x.copy_(latents.to(torch.float32) * s.init_noise_sigma)
         for i, t in enumerate(s.timesteps.tolist()):
             if teacher is not None:
                 x.copy_(teacher[i])
+            if scaled_input:
+                ops.axpby(x, x, s.input_scale(t), 0.0, out=ent["x"])
             ent["rb"].copy_(table[i])
             self._forward(ent, 2 * B, n_text, n_ip)
             if trace is not None:

@@ -6,6 +6,7 @@ alphas_cumprod / final_alpha_cumprod / order / config / from_config``.  ``step``
 (x_prev = c_x x + c_e eps with host-precomputed fp64 coefficients; no device->host sync, unlike the ~8 elementwise
 launches + CPU indexing of the original), and ``cfg_step`` additionally folds the classifier-free-guidance combine and
 the duplication of the next UNet input into the same pass (custom_pipelines.py:332-357).
+``B200EulerDiscreteScheduler`` is the SDXL pipelines' default (pipeline.py:101, refiner :128-131).
 ``B200DDPMScheduler`` is the prior's ancestral sampler (prior/model.py:134,585,648).
 """
 from __future__ import annotations
@@ -98,6 +99,59 @@ class B200DDIMScheduler(_SchedulerBase):
     def inverse_step(self, model_output, timestep, prev_timestep, sample):
         c_x, c_e = self.inverse_coefficients(timestep, prev_timestep)
         return ops.axpby(model_output, sample, c_x, c_e)
+
+
+class B200EulerDiscreteScheduler(_SchedulerBase):
+    """``EulerDiscreteScheduler`` of the SDXL pipelines (base pipeline default at pipeline.py:101, refiner at :128-131; SURVEY
+    8f-4): leading spacing, linear sigma interpolation, no churn.  Like DDIM it is linear in (x, eps) --
+    x_next = x + (sigma_next - sigma) eps, model input x / sqrt(sigma^2 + 1) -- so ``step`` / ``cfg_step`` reuse the fused
+    kernels with host-side fp64 coefficients; ``input_scale`` is applied by the sampler when it refreshes the UNet input."""
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        ac = self.alphas_cumprod.double()
+        self.all_sigmas = ((1 - ac) / ac) ** 0.5
+        self.sigmas = torch.cat([self.all_sigmas.flip(0), torch.zeros(1, dtype=torch.float64)]).float()
+        self.timesteps = torch.arange(self._cfg["num_train_timesteps"] - 1, -1, -1, dtype=torch.float32)
+
+    @property
+    def init_noise_sigma(self):
+        return float((float(self.sigmas.max()) ** 2 + 1) ** 0.5)
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        self.num_inference_steps = int(num_inference_steps)
+        ratio = self._cfg["num_train_timesteps"] // self.num_inference_steps
+        ts = (np.arange(0, self.num_inference_steps) * ratio).round()[::-1].copy().astype(np.float32) + self._cfg["steps_offset"]
+        sig = np.interp(ts, np.arange(0, len(self.all_sigmas)), self.all_sigmas.float().numpy())
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts)
+
+    def _sigmas_at(self, timestep):
+        i = int((self.timesteps == float(timestep)).nonzero()[0])
+        return float(self.sigmas[i]), float(self.sigmas[i + 1])
+
+    def input_scale(self, timestep):
+        sigma, _ = self._sigmas_at(timestep)
+        return 1.0 / math.sqrt(sigma * sigma + 1.0)
+
+    def scale_model_input(self, sample, timestep=None):
+        return ops.axpby(sample, sample, self.input_scale(timestep), 0.0)
+
+    def coefficients(self, timestep):
+        sigma, nxt = self._sigmas_at(timestep)
+        return 1.0, nxt - sigma
+
+    def step(self, model_output, timestep, sample, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, generator=None,
+             return_dict=False):
+        if s_churn != 0.0:
+            raise NotImplementedError("s_churn != 0 is not used by the reference pipelines")
+        c_x, c_e = self.coefficients(timestep)
+        prev = ops.axpby(model_output, sample.float(), c_x, c_e)
+        return SimpleNamespace(prev_sample=prev) if return_dict else (prev,)
+
+    def cfg_step(self, eps2, timestep, sample, guidance_scale, x_in_next2=None, out=None):
+        c_x, c_e = self.coefficients(timestep)
+        return ops.cfg_ddim_step(eps2, sample, guidance_scale, c_x, c_e, x_out=out, x_in_next2=x_in_next2)
 
 
 class B200DDPMScheduler(_SchedulerBase):

@@ -62,6 +62,15 @@ TINY_CONFIG = dict(sample_size=32, block_out_channels=(64, 128, 256), transforme
                    projection_class_embeddings_input_dim=6 * 32 + 128)
 
 
+# SDXL-refiner UNet (stabilityai/stable-diffusion-xl-refiner-1.0, loaded at pipeline.py:128-131 as ``piperf``): four
+# levels, attention on the two middle ones, 4 transformer layers per block, text context 1280, five micro-conditioning ids.
+REFINER_CONFIG = dict(block_out_channels=(384, 768, 1536, 1536), transformer_layers_per_block=(4, 4, 4, 4),
+                      attention_head_dim=(6, 12, 24, 24), cross_attention_dim=1280, addition_time_embed_dim=256,
+                      projection_class_embeddings_input_dim=2560,
+                      down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+                      up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"))
+
+
 # ------------------------------------------------------------------ parameter holders (names == diffusers names)
 class _Holder(nn.Module):
     def forward(self, *a, **k):  # pragma: no cover - never called: arithmetic lives in the CUDA library

@@ -150,3 +150,54 @@ def polar_interpolate(x, y, alpha):
     ll = x * alpha + y * (1 - alpha)
     n = n0 * alpha + n1 * (1 - alpha)
     return ll / ll.norm() * n
+
+
+class EulerDiscreteSchedulerOracle:
+    """Restated diffusers==0.26.3 ``EulerDiscreteScheduler`` with the SDXL scheduler config (the base pipeline's default at
+    pipeline.py:101 before serve.py:9 swaps in DDIM, and the refiner's scheduler at pipeline.py:128-131 / :358-361):
+    timestep_spacing "leading" + steps_offset 1, interpolation_type "linear", use_karras_sigmas False, s_churn 0 (the pipelines
+    pass no churn, so ``step`` is deterministic).  Parity unpinned (third-party); known answers pinned in
+    tests/test_oracle_structure.py: sigma_max = 14.6146, sigma_min = 0.0292 of the SDXL noise schedule."""
+    order = 1
+
+    def __init__(self, **kw):
+        cfg = dict(SDXL_SCHEDULER_CONFIG)
+        cfg.update(kw)
+        self.config = SimpleNamespace(**cfg)
+        self._cfg = cfg
+        self.alphas_cumprod = _alphas_cumprod(cfg)
+        self.all_sigmas = ((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5
+        self.sigmas = torch.cat([self.all_sigmas.flip(0), torch.zeros(1)])
+        self.timesteps = torch.arange(cfg["num_train_timesteps"] - 1, -1, -1, dtype=torch.float32)
+        self._step_index = None
+
+    @property
+    def init_noise_sigma(self):
+        return float((self.sigmas.max() ** 2 + 1) ** 0.5)          # "leading" spacing
+
+    def set_timesteps(self, n, device=None):
+        ts = _leading_timesteps(self._cfg, n).astype(np.float32)
+        sig = self.all_sigmas.numpy()
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts)
+        self._step_index = None
+
+    def _index(self, t):
+        if self._step_index is None:
+            self._step_index = int((self.timesteps == float(t)).nonzero()[0])
+        return self._step_index
+
+    def scale_model_input(self, sample, t):
+        sigma = self.sigmas[self._index(t)]
+        return sample / ((sigma ** 2 + 1) ** 0.5)
+
+    def step(self, model_output, t, sample, return_dict=False, **_):
+        i = self._index(t)
+        sigma = self.sigmas[i]
+        sample = sample.float()
+        pred_original = sample - sigma * model_output.float()
+        derivative = (sample - pred_original) / sigma
+        prev = sample + derivative * (self.sigmas[i + 1] - sigma)
+        self._step_index = i + 1
+        return (prev,)

@@ -55,6 +55,29 @@ def test_forward_parity_deep_narrow():
     assert e < EPS_TOL
 
 
+def test_forward_parity_refiner_topology():
+    """SDXL-refiner block layout (4 levels, attention on the middle two, 4 layers per block, plain text-only cross-attention,
+    five micro-conditioning ids) at narrow width: the same kernels with a different shape table."""
+    from instructany2pix_b200.unet import REFINER_CONFIG
+    from oracle.synth import synth_input, synth_state_dict
+    from oracle.unet import OracleUNet
+    cfg = UNetConfig(**{**REFINER_CONFIG, "sample_size": 32, "block_out_channels": (64, 128, 256, 256), "attention_head_dim": (1, 2, 4, 4),
+                        "transformer_layers_per_block": (2, 2, 2, 2), "cross_attention_dim": 128, "addition_time_embed_dim": 32,
+                        "projection_class_embeddings_input_dim": 5 * 32 + 96})
+    o = OracleUNet(cfg).eval()
+    o.load_state_dict(synth_state_dict(o, 21))
+    b = B200UNet.from_module(o, device="cuda")
+    x = synth_input("rf/x", (2, 4, 32, 32))
+    ctx = synth_input("rf/ctx", (2, 77, 128))
+    added = dict(text_embeds=synth_input("rf/pooled", (2, 96)), time_ids=torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0]] * 2))
+    for t in (601, 41):
+        ref = o(x, torch.tensor(t), ctx, added_cond_kwargs=added)[0]
+        out = b(cu(x), t, cu(ctx), added_cond_kwargs=cu(added))[0]
+        e = rel(out.cpu(), ref)
+        print(f"refiner-topology forward t={t}: eps rel-L2 = {e:.2e}")
+        assert e < EPS_TOL
+
+
 def test_quirk_and_plain_processors():
     o, b = build_pair(True, device="cuda")
     lat, ctx, added = make_inputs(TINY, B=1, L=16)
@@ -89,6 +112,38 @@ def test_sampler_parity(graph):
     ref_i = osampler.invert(o, lat, ctx[2:, :77], {k: v[2:] for k, v in added.items()}, num_inference_steps=4)
     out_i = s.invert(cu(lat), cu(ctx[2:, :77]), cu({k: v[2:] for k, v in added.items()}), num_inference_steps=4)
     assert rel(out_i.cpu(), ref_i) < 2e-2
+
+
+def test_sampler_parity_euler():
+    """EulerDiscreteScheduler (pipeline.py:101 default, refiner :128-131): model-input scaling by
+    1/sqrt(sigma^2+1), x += (sigma_next - sigma) eps, init_noise_sigma sqrt(sigma_max^2+1)."""
+    from instructany2pix_b200.scheduler import B200EulerDiscreteScheduler
+    from oracle.schedulers import EulerDiscreteSchedulerOracle
+    o, b = build_pair(True, device="cuda")
+    lat, ctx, added = make_inputs(TINY, B=2, L=16)
+    tr_o = []
+    ref = osampler.generate(o, lat, ctx, added, num_inference_steps=6, guidance_scale=7.5, trace=tr_o,
+                            scheduler=EulerDiscreteSchedulerOracle())
+    s = B200Sampler(b, scheduler=B200EulerDiscreteScheduler())
+    tr_b = []
+    s.generate(cu(lat), cu(ctx), cu(added), num_inference_steps=6, guidance_scale=7.5, trace=tr_b,
+               teacher=[t["x"].cuda() for t in tr_o])
+    worst = max(rel(a["eps2"].cpu(), r["eps2"]) for a, r in zip(tr_b, tr_o))
+    print(f"Euler teacher-forced per-step eps rel-L2: worst {worst:.2e}")
+    assert worst < EPS_TOL
+    free = s.generate(cu(lat), cu(ctx), cu(added), num_inference_steps=6, guidance_scale=7.5)
+    e = rel(free.cpu(), ref)
+    print(f"Euler free-running final latent rel-L2: {e:.2e}")
+    assert e < 5e-2
+    # the diffusers-style call surface: scale_model_input + step
+    sch, osch = B200EulerDiscreteScheduler(), EulerDiscreteSchedulerOracle()
+    sch.set_timesteps(6); osch.set_timesteps(6)
+    assert abs(sch.init_noise_sigma - osch.init_noise_sigma) < 1e-5
+    t = sch.timesteps[2]
+    osch._step_index = 2
+    x, eps = lat[:1], ctx[:1, :4, :16].reshape(1, 4, 4, 4).repeat(1, 1, 4, 4)
+    assert rel(sch.scale_model_input(cu(x), t).cpu(), osch.scale_model_input(x, t)) < 1e-6
+    assert rel(sch.step(cu(eps), t, cu(x))[0].cpu(), osch.step(eps, t, x)[0]) < 1e-6
 
 
 def test_decoded_image_psnr():
