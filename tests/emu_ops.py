@@ -147,6 +147,23 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
     return y.to(out_dtype)
 
 
+def conv_up2x(x, w4, cout, bias=None):
+    """four parity 2x2 convs over the low-res map with the pre-summed bf16 weights, exactly as the kernel evaluates them"""
+    assert x.dtype == BF and w4.dtype == BF
+    B, H, W, Cin = x.shape
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))                      # index (y + 1, x + 1)
+    out = torch.zeros(B, 2 * H, 2 * W, cout)
+    for py in range(2):
+        for px in range(2):
+            wk = w4[py * 2 + px].float().reshape(cout, 2, 2, Cin).permute(0, 3, 1, 2)      # taps (i, j)
+            y0, x0 = (0 if py == 0 else 1), (0 if px == 0 else 1)                          # first tap offset (-1 or 0) + pad 1
+            win = xp[:, :, y0:y0 + H + 1, x0:x0 + W + 1]
+            out[:, py::2, px::2, :] = F.conv2d(win, wk).permute(0, 2, 3, 1)
+    if bias is not None:
+        out = out + bias
+    return out
+
+
 def conv_in(x_nchw, w, bias, out_batch=None, out_dtype=BF):
     B = out_batch or x_nchw.shape[0]
     x = x_nchw.float().repeat(B // x_nchw.shape[0], 1, 1, 1)
