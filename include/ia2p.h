@@ -83,10 +83,14 @@ int ia2p_cast_to_bf16(const void* x, int x_dtype, void* y, int64_t n, void* stre
  * xa: [batch, hw, ca], xb: [batch, hw, cb] or NULL, both x_dtype (fp32|bf16); y: [batch, hw, ca+cb] bf16;
  * raw (nullable): [batch, hw, ca+cb] bf16 receives the un-normalised concat (operand of the fused 1x1 shortcut conv).
  * workspace: ia2p_groupnorm_workspace_bytes() of scratch (per-slab partial sums; results are bit-reproducible:
- * no atomics).  (ca+cb) % groups == 0, ca % 8 == cb % 8 == 0, ca+cb <= 4096. */
+ * no atomics).  (ca+cb) % groups == 0, ca % 8 == cb % 8 == 0, ca+cb <= 4096.
+ * cs_a / cs_b (nullable; both or neither when xb is given): the producers' column statistics (see `colstats` below) with
+ * cs_*_segments segments of batch * hw / 128 / segments tiles each; when given, the statistics pass over x is replaced by a
+ * reduction of those (hw % (128 * segments) == 0 required). */
 int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, int64_t cb, int x_dtype,
                         const float* gamma, const float* beta, void* y, void* raw,
                         int64_t batch, int64_t hw, int groups, float eps, int silu,
+                        const float* cs_a, int64_t cs_a_segments, const float* cs_b, int64_t cs_b_segments,
                         void* workspace, void* stream);
 int64_t ia2p_groupnorm_workspace_bytes(int64_t batch, int groups);
 
@@ -109,6 +113,16 @@ int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64
                    const float* bias, const float* rowbias, int64_t rows_per_batch,
                    const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue, void* stream);
 
+/* GroupNorm statistics from the producer (`colstats`, nullable, fp32-output calls of ia2p_gemm_ln_bf16 / ia2p_conv3x3_nhwc_bf16 /
+ * ia2p_conv_up2x_nhwc_bf16): [row tiles of 128 output pixels][N][2] receives each tile's per-column (sum, sum of squares), read
+ * back from the epilogue's staged slices, so the GroupNorm that consumes the tensor (ia2p_groupnorm_nhwc, cs_a / cs_b) needs no
+ * statistics pass over it.  Tiles follow the output pixel order (128 consecutive pixels; needs H*W % 128 == 0 to be usable by
+ * GroupNorm); conv_up2x writes 4 segments, one per output parity. */
+
+/* first dimension of a conv's `colstats` buffer for a [B, Ho, Wo] output grid (conv_up2x: per parity segment, on its input
+ * grid), or 0 when a 128-pixel tile would span several images and the statistics must not be requested; GEMMs: ceil(M / 128). */
+int64_t ia2p_conv_colstats_tiles(int64_t B, int64_t Ho, int64_t Wo);
+
 /* ia2p_gemm_bf16 + LayerNorm folding (replaces [3P] BasicTransformerBlock.norm1/2/3 followed by to_q/k/v, attn2.to_q and
  * the GEGLU projection -- SURVEY A.3 -- without a separate normalisation pass):
  *   PRODUCER (a GEMM writing the fp32 residual stream): out_bf16 (row pitch ldo2) receives a bf16 copy of the output rows and
@@ -121,7 +135,7 @@ int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, in
                       const void* W, void* out, int64_t ldo, int64_t M, int64_t N,
                       const float* bias, const float* rowbias, int64_t rows_per_batch,
                       const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue,
-                      void* out_bf16, int64_t ldo2, float* stats_out,
+                      void* out_bf16, int64_t ldo2, float* stats_out, float* colstats,
                       const float* ln_stats, int64_t ln_parts, const float* ln_c1, float ln_eps, void* stream);
 /* number of (sum, sumsq) partials per row a producer with N output columns writes */
 int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N);   /* depends on the tile width the producer picks for (M, N) */
@@ -135,13 +149,13 @@ int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N);   /* depends on the tile width
 int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int stride,
                            const void* w, const void* sc_a, int64_t sc_ca, const void* sc_b, int64_t sc_cb,
                            void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
-                           const void* residual, int res_dtype, void* stream);
+                           const void* residual, int res_dtype, float* colstats, void* stream);
 
 /* Nearest-2x upsample + 3x3 pad-1 conv in one op ([3P] Upsample2D = F.interpolate(scale_factor=2, "nearest") -> conv; UNet up
  * blocks, VAE decoder): four 2x2 convs over the LOW-resolution map, one per output parity, with pre-summed weights
  * w4 [4][Cout][4*Cin] bf16 (instructany2pix_b200.packing.pack_conv3x3_up2x).  x [B,H,W,Cin] bf16 -> out [B,2H,2W,Cout] fp32. */
 int ia2p_conv_up2x_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w4, void* out,
-                             int64_t Cout, const float* bias, void* stream);
+                             int64_t Cout, const float* bias, float* colstats, void* stream);
 
 /* Stride-2 3x3 conv with padding only at the bottom / right (input index 2*o + k): the VAE encoder's Downsample2D
  * ([3P] diffusers: padding=0 after F.pad(x, (0,1,0,1)); reached from vae.encode at ddim/pnp_pipeline.py:195-204). */

@@ -30,15 +30,16 @@ SIGNATURES = {
     "ia2p_timestep_embedding": ([_p, _l, _i, _i, _f, _p, _i, _p], _i),
     "ia2p_upsample2x_nhwc": ([_p, _i, _p, _l, _l, _l, _l, _p], _i),
     "ia2p_cast_to_bf16": ([_p, _i, _p, _l, _p], _i),
-    "ia2p_groupnorm_nhwc": ([_p, _l, _p, _l, _i, _p, _p, _p, _p, _l, _l, _i, _f, _i, _p, _p], _i),
+    "ia2p_groupnorm_nhwc": ([_p, _l, _p, _l, _i, _p, _p, _p, _p, _l, _l, _i, _f, _i, _p, _l, _p, _l, _p, _p], _i),
     "ia2p_groupnorm_workspace_bytes": ([_l, _i], _l),
     "ia2p_layernorm": ([_p, _i, _p, _p, _p, _i, _l, _l, _f, _p], _i),
     "ia2p_gemm_bf16": ([_p, _l, _l, _p, _l, _l, _p, _p, _l, _l, _l, _p, _p, _l, _p, _l, _i, _i, _i, _p], _i),
     "ia2p_gemm_ln_bf16": ([_p, _l, _l, _p, _l, _l, _p, _p, _l, _l, _l, _p, _p, _l, _p, _l, _i, _i, _i,
-                           _p, _l, _p, _p, _l, _p, _f, _p], _i),
+                           _p, _l, _p, _p, _p, _l, _p, _f, _p], _i),
     "ia2p_gemm_ln_parts": ([_l, _l], _l),
-    "ia2p_conv3x3_nhwc_bf16": ([_p, _l, _l, _l, _l, _i, _p, _p, _l, _p, _l, _p, _i, _l, _p, _p, _p, _i, _p], _i),
-    "ia2p_conv_up2x_nhwc_bf16": ([_p, _l, _l, _l, _l, _p, _p, _l, _p, _p], _i),
+    "ia2p_conv_colstats_tiles": ([_l, _l, _l], _l),
+    "ia2p_conv3x3_nhwc_bf16": ([_p, _l, _l, _l, _l, _i, _p, _p, _l, _p, _l, _p, _i, _l, _p, _p, _p, _i, _p, _p], _i),
+    "ia2p_conv_up2x_nhwc_bf16": ([_p, _l, _l, _l, _l, _p, _p, _l, _p, _p, _p], _i),
     "ia2p_conv3x3_s2_padend_nhwc_bf16": ([_p, _l, _l, _l, _l, _p, _p, _i, _l, _p, _p], _i),
     "ia2p_gaussian_sample": ([_p, _p, _p, _l, _l, _l, _f, _p], _i),
     "ia2p_conv_in_nchw": ([_p, _i, _l, _l, _l, _l, _l, _p, _p, _p, _i, _l, _p], _i),

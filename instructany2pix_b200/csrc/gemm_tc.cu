@@ -58,6 +58,7 @@ struct TcParams {
   __nv_bfloat16* out2;             // producer: bf16 copy of out (row pitch ldo2) | NULL
   long long ldo2;
   float* stats_out;                // producer: [rows][2 * n_tiles][2] partial sums | NULL
+  float* colstats;                 // EPI >= 1: [m_tiles][N][2] per-tile column (sum, sum of squares) for a following GroupNorm | NULL
   const float* ln_stats;           // consumer: [rows][ln_parts][2] | NULL
   const float* ln_c1;              // consumer: [N]  (row sums of the gamma-scaled weight)
   int ln_parts;
@@ -450,6 +451,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int i = 0; i < 16; ++i) { st_sum += f[i]; st_sq += f[i] * f[i]; }
           }
+          if (p.colstats != nullptr && !valid) {                // rows outside the output must not count in the column sums
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = 0.f;
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) sts128(f_row + (((uint32_t)j ^ sw64) << 4), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           if (p.out2 != nullptr) {
@@ -464,6 +469,28 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             tma_store_4d(&maps.o, f_row - row * 64, n, x0, y0, b0);
             if (p.out2 != nullptr) tma_store_4d(&maps.o2, h_row - row * 32, n, x0, y0, b0);
             bulk_commit_group();
+          }
+          if (p.colstats != nullptr) {
+            // GroupNorm statistics for free: column sums of the staged slice over the tile's 128 rows.  Warp wq of the
+            // half-group owns columns 4 wq .. 4 wq + 3 (one 16-byte chunk); lane = (row phase 0..7, column 0..3) walks rows
+            // phase + 8 i, which the SWIZZLE_64B layout spreads over all 32 banks; three shuffles fold the 8 phases.
+            const uint32_t wq = (uint32_t)(warp - 2) & 3u, cc = (uint32_t)lane & 3u, r0 = (uint32_t)lane >> 2;
+            const uint32_t fb = f_row - row * 64;
+            float cs = 0.f, cq = 0.f;
+#pragma unroll
+            for (uint32_t i = 0; i < 16; ++i) {
+              const uint32_t r = r0 + 8u * i;
+              const float v = lds32(fb + r * 64u + ((wq ^ ((r >> 1) & 3u)) << 4) + cc * 4u);
+              cs += v;
+              cq += v * v;
+            }
+#pragma unroll
+            for (int o = 4; o <= 16; o <<= 1) {
+              cs += __shfl_xor_sync(0xffffffffu, cs, o);
+              cq += __shfl_xor_sync(0xffffffffu, cq, o);
+            }
+            if (lane < 4 && m_tile < p.m_tiles)
+              *reinterpret_cast<float2*>(p.colstats + ((long long)m_tile * p.N + n + 4 * (int)wq + lane) * 2) = make_float2(cs, cq);
           }
           ++g;
         }
@@ -974,7 +1001,7 @@ extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void
                               const float* bias, const float* rowbias, int64_t rows_per_batch,
                               const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue, void* stream) {
   return ia2p_gemm_ln_bf16(A, lda, K1, A2, lda2, K2, W, out, ldo, M, N, bias, rowbias, rows_per_batch, residual, ldr, res_dtype,
-                           out_dtype, epilogue, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, stream);
+                           out_dtype, epilogue, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0.f, stream);
 }
 
 extern "C" int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N) {
@@ -986,7 +1013,7 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
                                  const void* W, void* out, int64_t ldo, int64_t M, int64_t N,
                                  const float* bias, const float* rowbias, int64_t rows_per_batch,
                                  const void* residual, int64_t ldr, int res_dtype, int out_dtype, int epilogue,
-                                 void* out_bf16, int64_t ldo2, float* stats_out,
+                                 void* out_bf16, int64_t ldo2, float* stats_out, float* colstats,
                                  const float* ln_stats, int64_t ln_parts, const float* ln_c1, float ln_eps, void* stream) {
   if (int e = check_device()) return e;
   IA2P_REQUIRE((ln_stats == nullptr) == (ln_c1 == nullptr) && (ln_stats == nullptr || (ln_parts > 0 && ln_parts <= 256)), IA2P_E_ARG,
@@ -1047,6 +1074,8 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
   p.ldo = ldo; p.ldr = ldr; p.geglu = geglu ? 1 : 0;
   p.out_f32 = out_dtype == IA2P_F32; p.res_f32 = res_dtype == IA2P_F32;
   p.out2 = static_cast<__nv_bfloat16*>(out_bf16); p.ldo2 = ldo2; p.stats_out = stats_out;
+  IA2P_REQUIRE(colstats == nullptr || (out_dtype == IA2P_F32 && !geglu), IA2P_E_ARG, "gemm: column statistics need the fp32-output epilogue");
+  p.colstats = colstats;
   p.ln_stats = ln_stats; p.ln_c1 = ln_c1; p.ln_parts = (int)ln_parts;
   p.ln_inv_n = 1.0f / (float)(K1 + K2); p.ln_eps = ln_eps;
   return dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream));
@@ -1055,7 +1084,7 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
 static int conv3x3_impl(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int stride, bool pad_end,
                         const void* w, const void* sc_a, int64_t sc_ca, const void* sc_b, int64_t sc_cb,
                         void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
-                        const void* residual, int res_dtype, void* stream) {
+                        const void* residual, int res_dtype, float* colstats, void* stream) {
   if (int e = check_device()) return e;
   IA2P_REQUIRE((out_dtype == IA2P_BF16 || out_dtype == IA2P_F32) && (residual == nullptr || res_dtype == IA2P_BF16 || res_dtype == IA2P_F32),
                IA2P_E_ARG, "conv3x3: out/residual dtype must be bf16 or f32");
@@ -1131,21 +1160,23 @@ static int conv3x3_impl(const void* x, int64_t B, int64_t H, int64_t W, int64_t 
   p.out = out;
   p.ldo = Cout; p.ldr = Cout; p.geglu = 0;
   p.out_f32 = out_dtype == IA2P_F32; p.res_f32 = res_dtype == IA2P_F32;
+  IA2P_REQUIRE(colstats == nullptr || (p.out_f32 && tma_epilogue(p)), IA2P_E_ARG, "conv3x3: column statistics need the fp32-output epilogue");
+  p.colstats = colstats;
   return dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ia2p_conv3x3_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int stride,
                                       const void* w, const void* sc_a, int64_t sc_ca, const void* sc_b, int64_t sc_cb,
                                       void* out, int out_dtype, int64_t Cout, const float* bias, const float* rowbias,
-                                      const void* residual, int res_dtype, void* stream) {
+                                      const void* residual, int res_dtype, float* colstats, void* stream) {
   return conv3x3_impl(x, B, H, W, Cin, stride, false, w, sc_a, sc_ca, sc_b, sc_cb, out, out_dtype, Cout, bias, rowbias, residual,
-                      res_dtype, stream);
+                      res_dtype, colstats, stream);
 }
 
 extern "C" int ia2p_conv3x3_s2_padend_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w,
                                                 void* out, int out_dtype, int64_t Cout, const float* bias, void* stream) {
   return conv3x3_impl(x, B, H, W, Cin, 2, true, w, nullptr, 0, nullptr, 0, out, out_dtype, Cout, bias, nullptr, nullptr, IA2P_BF16,
-                      stream);
+                      nullptr, stream);
 }
 
 // Nearest-2x upsample folded into the following 3x3 conv ([3P] Upsample2D: F.interpolate(x, scale 2, "nearest") -> conv).  An output
@@ -1154,7 +1185,7 @@ extern "C" int ia2p_conv3x3_s2_padend_nhwc_bf16(const void* x, int64_t B, int64_
 // w4: [4 parities (py*2+px)][Cout][4*Cin] bf16, tap order (row tap, col tap); out: [B, 2H, 2W, Cout] fp32 (TMA-store epilogue
 // with a stride-2 output map per parity).
 extern "C" int ia2p_conv_up2x_nhwc_bf16(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w4, void* out,
-                                        int64_t Cout, const float* bias, void* stream) {
+                                        int64_t Cout, const float* bias, float* colstats, void* stream) {
   if (int e = check_device()) return e;
   IA2P_REQUIRE(x && w4 && out && B > 0 && H > 0 && W > 0, IA2P_E_ARG, "conv_up2x: null pointer or empty shape");
   IA2P_REQUIRE(Cin % 64 == 0 && Cout % 32 == 0, IA2P_E_SHAPE, "conv_up2x: Cin %% 64 == 0 and Cout %% 32 == 0 required");
@@ -1194,8 +1225,20 @@ extern "C" int ia2p_conv_up2x_nhwc_bf16(const void* x, int64_t B, int64_t H, int
     p.ldo = Cout; p.ldr = Cout;
     p.ost_x = 2 * Cout; p.ost_y = 4 * W * Cout; p.ost_b = 4 * H * W * Cout;
     p.out_f32 = 1; p.res_f32 = 0; p.geglu = 0;
+    p.colstats = colstats == nullptr ? nullptr : colstats + (size_t)par * p.m_tiles * Cout * 2;   // one segment per output parity
     IA2P_REQUIRE(tma_epilogue(p), IA2P_E_ARG, "conv_up2x needs the TMA-store epilogue (IA2P_GEMM_EPI=0 is set)");
     if (int e = dispatch_tc(maps, p, bn, static_cast<cudaStream_t>(stream))) return e;
   }
   return 0;
+}
+
+// Row tiles the conv kernels cut a [B, Ho, Wo] output pixel grid into, i.e. the first dimension of a `colstats` buffer -- or 0 when
+// a tile would span several images (Ho * Wo has too few factors of two for a 128-pixel tile), in which case the column
+// statistics cannot serve a per-image GroupNorm and must not be requested.  Plain GEMMs use ceil(M / 128) row tiles.
+extern "C" int64_t ia2p_conv_colstats_tiles(int64_t B, int64_t Ho, int64_t Wo) {
+  if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
+  int TW = 1; while (TW < 128 && Wo % (TW * 2) == 0) TW *= 2;
+  int TH = 1; while (TW * TH < 128 && Ho % (TH * 2) == 0) TH *= 2;
+  if (TW * TH != 128) return 0;
+  return (Wo / TW) * (Ho / TH) * B;
 }

@@ -93,12 +93,53 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const T* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------- GroupNorm statistics from the producers' column sums
+// The tcgen05 GEMM / conv epilogue can emit per-tile (128 pixels) per-channel (sum, sum of squares) of its fp32 output
+// (TcParams::colstats); this kernel folds them into the per-(image, group) partials gn_apply_kernel expects (one "slab"), so the
+// statistics pass over the activation disappears.  One CTA per (group, image); fixed summation order -> bit-reproducible.
+__global__ void __launch_bounds__(128) gn_colstats_reduce_kernel(const float* __restrict__ csa, int ca, int sega,
+                                                                 const float* __restrict__ csb, int cb, int segb, int tiles_per_image,
+                                                                 int batch, int groups, double* __restrict__ partials) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int C = ca + cb, cpg = C / groups;
+  double s = 0.0, q = 0.0;
+  // work items: (tile of the image, channel of the group); a channel lives in source a or b
+  const int items = tiles_per_image * cpg;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int t = it / cpg, c = g * cpg + (it - t * cpg);
+    const bool in_a = c < ca;
+    const float* cs = in_a ? csa : csb;
+    const int cw = in_a ? ca : cb, cc = in_a ? c : c - ca, seg = in_a ? sega : segb;
+    const int tps = tiles_per_image / seg;                          // tiles of one image inside one segment
+    const int sidx = t / tps, tin = t - sidx * tps;
+    const long long tile = (long long)sidx * batch * tps + (long long)b * tps + tin;
+    const float2 v = *reinterpret_cast<const float2*>(cs + (tile * cw + cc) * 2);
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  __shared__ double red[2][4];
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* dst = partials + ((long long)b * groups + g) * 2;
+    dst[0] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    dst[1] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+  }
+}
+
 // ---------------------------------------------------------------- GroupNorm apply (+SiLU)
 template <typename T>
 __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const T* __restrict__ xa, int ca, const T* __restrict__ xb, int cb,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw, long long hw, int groups,
-                                float eps, int silu, int pix_per_slab, const double* __restrict__ partials) {
+                                float eps, int silu, int pix_per_slab, const double* __restrict__ partials, int nslabs) {
   pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
   pdl_wait();
   extern __shared__ float sm[];   // scale[C], shift[C], then mean[groups], rstd[groups]
@@ -116,8 +157,8 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const T* __restrict__ 
     const int lane = tid & 31, wid = tid >> 5, nwarps = (nthr + 31) >> 5;
     for (int g = wid; g < groups; g += nwarps) {
       double a = 0.0, q = 0.0;
-      for (int sl = lane; sl < (int)gridDim.x; sl += 32) {
-        const double2 v = *reinterpret_cast<const double2*>(partials + ((b * gridDim.x + sl) * groups + g) * 2);
+      for (int sl = lane; sl < nslabs; sl += 32) {
+        const double2 v = *reinterpret_cast<const double2*>(partials + ((b * nslabs + sl) * groups + g) * 2);
         a += v.x;
         q += v.y;
       }
@@ -251,7 +292,8 @@ extern "C" int64_t ia2p_groupnorm_workspace_bytes(int64_t batch, int groups) {
 
 extern "C" int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, int64_t cb, int x_dtype, const float* gamma,
                                    const float* beta, void* y, void* raw, int64_t batch, int64_t hw, int groups, float eps,
-                                   int silu, void* workspace, void* stream) {
+                                   int silu, const float* cs_a, int64_t cs_a_segments, const float* cs_b, int64_t cs_b_segments,
+                                   void* workspace, void* stream) {
   if (int e = check_device()) return e;
   IA2P_REQUIRE(x_dtype == IA2P_BF16 || x_dtype == IA2P_F32, IA2P_E_ARG, "groupnorm: x_dtype must be bf16 or f32");
   IA2P_REQUIRE(xa && gamma && beta && y && workspace && batch > 0 && hw > 0 && groups > 0, IA2P_E_ARG, "groupnorm: bad arguments");
@@ -278,16 +320,27 @@ extern "C" int ia2p_groupnorm_nhwc(const void* xa, int64_t ca, const void* xb, i
   double* stats = static_cast<double*>(workspace);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   __nv_bfloat16* rp = static_cast<__nv_bfloat16*>(raw);
+  // statistics: either from the producers' column sums (one reduction CTA per (group, image), nslabs = 1) or by a pass over x
+  const bool from_cs = cs_a != nullptr;
+  int nslabs = (int)slabs;
+  if (from_cs) {
+    IA2P_REQUIRE(cb == 0 || cs_b != nullptr, IA2P_E_ARG, "groupnorm: column statistics must be given for both sources");
+    const int64_t sa = cs_a_segments > 0 ? cs_a_segments : 1, sb = cs_b_segments > 0 ? cs_b_segments : 1;
+    IA2P_REQUIRE(hw % (128 * sa) == 0 && hw % (128 * sb) == 0, IA2P_E_SHAPE, "groupnorm: column statistics need hw %% (128 * segments) == 0");
+    IA2P_CUDA(launch_pdl(gn_colstats_reduce_kernel, dim3((unsigned)groups, (unsigned)batch), dim3(128), 0, st, cs_a, (int)ca, (int)sa,
+                         cs_b, (int)cb, (int)sb, (int)(hw / 128), (int)batch, groups, stats));
+    nslabs = 1;
+  }
   if (x_dtype == IA2P_BF16) {
     const __nv_bfloat16 *a = static_cast<const __nv_bfloat16*>(xa), *b = static_cast<const __nv_bfloat16*>(xb);
-    launch_pdl(gn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(block), smem_stats, st, a, (int)ca, b, (int)cb, hw, groups, pps, stats);
+    if (!from_cs) launch_pdl(gn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(block), smem_stats, st, a, (int)ca, b, (int)cb, hw, groups, pps, stats);
     IA2P_LAUNCH_CHECK();
-    launch_pdl(gn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(block), smem, st, a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
+    launch_pdl(gn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(block), smem, st, a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, (const double*)stats, nslabs);
   } else {
     const float *a = static_cast<const float*>(xa), *b = static_cast<const float*>(xb);
-    launch_pdl(gn_stats_kernel<float>, dim3(grid), dim3(block), smem_stats, st, a, (int)ca, b, (int)cb, hw, groups, pps, stats);
+    if (!from_cs) launch_pdl(gn_stats_kernel<float>, dim3(grid), dim3(block), smem_stats, st, a, (int)ca, b, (int)cb, hw, groups, pps, stats);
     IA2P_LAUNCH_CHECK();
-    launch_pdl(gn_apply_kernel<float>, dim3(grid), dim3(block), smem, st, a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, stats);
+    launch_pdl(gn_apply_kernel<float>, dim3(grid), dim3(block), smem, st, a, (int)ca, b, (int)cb, gamma, beta, yp, rp, hw, groups, eps, silu, pps, (const double*)stats, nslabs);
   }
   IA2P_LAUNCH_CHECK();
   return 0;

@@ -6,6 +6,8 @@ PyTorch/CPU implementation: a missing library or a non-sm_100 device raises ``IA
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -23,6 +25,8 @@ def _stream():
 LAUNCHES = 0
 PROFILE = None
 TAG_ALWAYS = False          # tools/timeline_step.py: build the shape tags without event profiling
+# GroupNorm statistics from the producing GEMM / conv epilogue (False or IA2P_COLSTATS=0: separate statistics pass over x)
+USE_COLSTATS = os.environ.get("IA2P_COLSTATS", "1") != "0"
 _KERNELS_PER_CALL = {"ia2p_groupnorm_nhwc": 2, "ia2p_conv_up2x_nhwc_bf16": 4, "ia2p_polar_interpolate": 2}
 _FLOPS = 0.0
 _BYTES = 0.0                # algorithmic bytes of the call (operands read once + results written once), for bench.py's roofline
@@ -194,9 +198,18 @@ def groupnorm(xa, xb, gamma, beta, groups, eps, silu, want_raw=False):
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 4096), device=xa.device, dtype=torch.uint8)
         _GN_WS[key] = ws
+    # statistics straight from the producers' epilogues when every source carries them (attached by gemm / conv3x3 / conv_up2x)
+    csa, csb = getattr(xa, "_ia2p_cs", None), (None if xb is None else getattr(xb, "_ia2p_cs", None))
+    use_cs = USE_COLSTATS and csa is not None and (xb is None or csb is not None)
+    if use_cs:
+        use_cs = hw % (128 * csa[1]) == 0 and (csb is None or hw % (128 * csb[1]) == 0)
+    if not use_cs:
+        csa = csb = None
     _run(lib.ia2p_groupnorm_nhwc, (xa.data_ptr(), ca, _ptr(xb), cb, _DT[xa.dtype], gamma.data_ptr(), beta.data_ptr(),
-                                       out.data_ptr(), _ptr(raw), b, hw, groups, float(eps), int(silu), ws.data_ptr(),
-                                       _stream()), "groupnorm")
+                                       out.data_ptr(), _ptr(raw), b, hw, groups, float(eps), int(silu),
+                                       0 if csa is None else csa[0].data_ptr(), 1 if csa is None else csa[1],
+                                       0 if csb is None else csb[0].data_ptr(), 1 if csb is None else csb[1],
+                                       ws.data_ptr(), _stream()), "groupnorm")
     return (out, raw) if want_raw else out
 
 
@@ -218,8 +231,13 @@ def layernorm(x, gamma, beta, eps, out_dtype=None):
 
 
 # ------------------------------------------------------------------------------------------------ tensor-core GEMM / conv
+def _colstats_buffer(tiles, n, device):
+    """[row tiles][n][2] fp32 for the per-tile column sums a producer epilogue emits (consumed by groupnorm); None if tiles == 0"""
+    return torch.empty(tiles, n, 2, device=device, dtype=torch.float32) if tiles > 0 else None
+
+
 def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None, geglu=False, out=None,
-         out_dtype=torch.bfloat16, want_ln=False, ln=None):
+         out_dtype=torch.bfloat16, want_ln=False, ln=None, want_colstats=False):
     """out = epilogue([a | a2] @ w^T).  a: [M,K1] bf16 (row-strided view allowed), w: [N,K1+K2] bf16 contiguous;
     residual bf16|fp32, out bf16|fp32 (fp32 = residual-stream tensors).
 
@@ -257,6 +275,7 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
         assert not geglu
         out2 = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
         stats = torch.empty(M, int(lib.ia2p_gemm_ln_parts(M, N)), 2, device=a.device, dtype=torch.float32)
+    cs = _colstats_buffer((M + 127) // 128, N, a.device) if (want_colstats and USE_COLSTATS and out.dtype == torch.float32 and not geglu) else None
     ln_stats = ln_c1 = None
     ln_parts, ln_eps = 0, 0.0
     if ln is not None:
@@ -274,14 +293,17 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
     _run(lib.ia2p_gemm_ln_bf16, (a.data_ptr(), lda, K1, _ptr(a2), lda2, K2, w.data_ptr(), out.data_ptr(), ldo, M, N,
                                   _ptr(bias), _ptr(rowbias), int(rows_per_batch), _ptr(residual), ldr, res_dt,
                                   _DT[out.dtype], _lib.EPI_GEGLU if geglu else _lib.EPI_NONE,
-                                  _ptr(out2), N, _ptr(stats), _ptr(ln_stats), ln_parts, _ptr(ln_c1), float(ln_eps),
+                                  _ptr(out2), N, _ptr(stats), _ptr(cs), _ptr(ln_stats), ln_parts, _ptr(ln_c1), float(ln_eps),
                                   _stream()), "gemm_bf16")
+    if cs is not None:
+        out._ia2p_cs = (cs, 1)
     if want_ln:
         return out, out2, stats
     return out
 
 
-def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None, residual=None, out_dtype=torch.bfloat16):
+def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None, residual=None, out_dtype=torch.bfloat16,
+            want_colstats=False):
     """3x3 pad-1 conv on NHWC bf16; w: [cout, 9*Cin + Csc] bf16, K order (ky,kx,cin) then shortcut channels;
     residual bf16|fp32, out bf16|fp32."""
     lib = _lib.load()
@@ -313,13 +335,18 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
               + (residual.numel() * residual.element_size() if residual is not None else 0))
     if PROFILE is not None or TAG_ALWAYS:
         _TAG = f"conv {H}x{W} C{Cin}->{cout} K{w.shape[1]} s{stride}{' res' if residual is not None else ''} out{str(out_dtype)[6:]}"
+    cs = None
+    if want_colstats and USE_COLSTATS and out_dtype == torch.float32:
+        cs = _colstats_buffer(int(lib.ia2p_conv_colstats_tiles(B, Ho, Wo)), cout, x.device)
     _run(lib.ia2p_conv3x3_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, stride, w.data_ptr(), _ptr(sc_a), ca, _ptr(sc_b), cb,
                                           out.data_ptr(), _DT[out_dtype], cout, _ptr(bias), _ptr(rowbias), _ptr(residual),
-                                          res_dt, _stream()), "conv3x3")
+                                          res_dt, _ptr(cs), _stream()), "conv3x3")
+    if cs is not None:
+        out._ia2p_cs = (cs, 1)
     return out
 
 
-def conv_up2x(x, w4, cout, bias=None):
+def conv_up2x(x, w4, cout, bias=None, want_colstats=False):
     """nearest-2x upsample + 3x3 conv as four parity 2x2 convs over the low-res map; x NHWC bf16, w4 [4, cout, 4*Cin] bf16
     (packing.pack_conv3x3_up2x) -> [B, 2H, 2W, cout] fp32."""
     lib = _lib.load()
@@ -335,8 +362,11 @@ def conv_up2x(x, w4, cout, bias=None):
     _BYTES = 2.0 * B * H * W * Cin + 2.0 * w4.numel() + 4.0 * out.numel()
     if PROFILE is not None or TAG_ALWAYS:
         _TAG = f"conv_up2x {H}x{W}->{2 * H}x{2 * W} C{Cin}->{cout} (4 x K{4 * Cin})"
-    _run(lib.ia2p_conv_up2x_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, w4.data_ptr(), out.data_ptr(), cout, _ptr(bias), _stream()),
-         "conv_up2x")
+    cs = _colstats_buffer(4 * int(lib.ia2p_conv_colstats_tiles(B, H, W)), cout, x.device) if (want_colstats and USE_COLSTATS) else None
+    _run(lib.ia2p_conv_up2x_nhwc_bf16, (x.data_ptr(), B, H, W, Cin, w4.data_ptr(), out.data_ptr(), cout, _ptr(bias), _ptr(cs),
+                                            _stream()), "conv_up2x")
+    if cs is not None:
+        out._ia2p_cs = (cs, 4)                 # one segment of row tiles per output parity
     return out
 
 

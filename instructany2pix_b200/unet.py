@@ -521,14 +521,14 @@ class B200UNet(nn.Module):
             else:
                 h = ops.groupnorm(x, skip, p["g1"], p["b1"], G, cfg.norm_eps, True)
             lo, hi = p["temb_slice"]
-            h = ops.conv3x3(h, p["w1"], p["w1"].shape[0], rowbias=rowbias[:, lo:hi].contiguous(), out_dtype=SD)
+            h = ops.conv3x3(h, p["w1"], p["w1"].shape[0], rowbias=rowbias[:, lo:hi].contiguous(), out_dtype=SD, want_colstats=True)
             h = ops.groupnorm(h, None, p["g2"], p["b2"], G, cfg.norm_eps, True)
             if p["has_sc"]:
                 if raw is not None:
-                    return ops.conv3x3(h, p["w2"], p["w2"].shape[0], sc_a=raw, bias=p["cb2"], out_dtype=SD)
-                return ops.conv3x3(h, p["w2"], p["w2"].shape[0], sc_a=x, sc_b=skip, bias=p["cb2"], out_dtype=SD)
+                    return ops.conv3x3(h, p["w2"], p["w2"].shape[0], sc_a=raw, bias=p["cb2"], out_dtype=SD, want_colstats=True)
+                return ops.conv3x3(h, p["w2"], p["w2"].shape[0], sc_a=x, sc_b=skip, bias=p["cb2"], out_dtype=SD, want_colstats=True)
             assert skip is None
-            return ops.conv3x3(h, p["w2"], p["w2"].shape[0], bias=p["cb2"], residual=x, out_dtype=SD)
+            return ops.conv3x3(h, p["w2"], p["w2"].shape[0], bias=p["cb2"], residual=x, out_dtype=SD, want_colstats=True)
 
         def transformer(name, mod, x):
             p = P[name]
@@ -577,8 +577,12 @@ class B200UNet(nn.Module):
                     # the last block's output is consumed only by proj_out as a tensor-core operand: write it as bf16
                     last = k == nblk - 1
                     t = ops.gemm(h, q["wf"], bias=q["bf"], residual=t, out_dtype=BF if last else SD)
-            out = ops.gemm(t, p["wo"], bias=p["bo"], residual=x.reshape(M, C), out_dtype=SD)
-            return out.reshape(Bx, H, W, C)
+            out = ops.gemm(t, p["wo"], bias=p["bo"], residual=x.reshape(M, C), out_dtype=SD, want_colstats=True)
+            cs = getattr(out, "_ia2p_cs", None)
+            out = out.reshape(Bx, H, W, C)
+            if cs is not None:
+                out._ia2p_cs = cs              # GroupNorm statistics of the next block come from this epilogue
+            return out
 
         w_in, b_in = P["conv_in"]
         x = ops.conv_in(sample, w_in, b_in, out_batch=batch, out_dtype=SD)
@@ -591,7 +595,7 @@ class B200UNet(nn.Module):
                 skips.append(x)
             if hasattr(blk, "downsamplers"):
                 p = P[f"down_blocks.{i}.downsamplers.0"]
-                x = ops.conv3x3(ops.to_bf16(x), p["w"], p["w"].shape[0], stride=2, bias=p["b"], out_dtype=SD)
+                x = ops.conv3x3(ops.to_bf16(x), p["w"], p["w"].shape[0], stride=2, bias=p["b"], out_dtype=SD, want_colstats=True)
                 skips.append(x)
         x = resnet("mid_block.resnets.0", x)
         x = transformer("mid_block.attentions.0", self.mid_block.attentions[0], x)
@@ -604,7 +608,7 @@ class B200UNet(nn.Module):
             if hasattr(blk, "upsamplers"):
                 p = P[f"up_blocks.{i}.upsamplers.0"]
                 if SD == torch.float32 and self.fold_upsample:
-                    x = ops.conv_up2x(ops.to_bf16(x), p["w4"], p["w"].shape[0], bias=p["b"])
+                    x = ops.conv_up2x(ops.to_bf16(x), p["w4"], p["w"].shape[0], bias=p["b"], want_colstats=True)
                 else:
                     x = ops.conv3x3(ops.upsample2x(x), p["w"], p["w"].shape[0], bias=p["b"], out_dtype=SD)
         g, b = P["norm_out"]

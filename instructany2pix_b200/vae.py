@@ -195,11 +195,11 @@ class B200VAE(nn.Module):
             h, raw = ops.groupnorm(x, None, p["g1"], p["b1"], G, 1e-6, True, want_raw=True)
         else:
             h = ops.groupnorm(x, None, p["g1"], p["b1"], G, 1e-6, True)
-        h = ops.conv3x3(h, p["w1"], p["w1"].shape[0], bias=p["cb1"], out_dtype=torch.float32)
+        h = ops.conv3x3(h, p["w1"], p["w1"].shape[0], bias=p["cb1"], out_dtype=torch.float32, want_colstats=True)
         h = ops.groupnorm(h, None, p["g2"], p["b2"], G, 1e-6, True)
         if p["has_sc"]:
-            return ops.conv3x3(h, p["w2"], p["w2"].shape[0], sc_a=raw, bias=p["cb2"], out_dtype=torch.float32)
-        return ops.conv3x3(h, p["w2"], p["w2"].shape[0], bias=p["cb2"], residual=x, out_dtype=torch.float32)
+            return ops.conv3x3(h, p["w2"], p["w2"].shape[0], sc_a=raw, bias=p["cb2"], out_dtype=torch.float32, want_colstats=True)
+        return ops.conv3x3(h, p["w2"], p["w2"].shape[0], bias=p["cb2"], residual=x, out_dtype=torch.float32, want_colstats=True)
 
     def _attn(self, P, name, x):
         """single head, head_dim = C ([3P] Attention with heads=1): softmax(q k^T / sqrt C) v, residual add in to_out's epilogue."""
@@ -242,7 +242,7 @@ class B200VAE(nn.Module):
                 x = self._res(P, f"decoder.up_blocks.{i}.resnets.{j}", x)
             if hasattr(blk, "upsamplers"):
                 q = P[f"decoder.up_blocks.{i}.upsamplers.0"]
-                x = ops.conv_up2x(ops.to_bf16(x), q["w4"], q["w"].shape[0], bias=q["b"])     # Upsample2D: nearest 2x + conv, folded
+                x = ops.conv_up2x(ops.to_bf16(x), q["w4"], q["w"].shape[0], bias=q["b"], want_colstats=True)   # Upsample2D folded
         h = ops.groupnorm(x, None, *P["decoder.norm_out"], G, 1e-6, True)
         return ops.conv_out(h, *P["decoder.conv_out"], out_dtype=torch.float32)
 

@@ -98,7 +98,7 @@ def layernorm(x, gamma, beta, eps, out_dtype=None):
 
 
 def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None, geglu=False, out=None, out_dtype=BF,
-         want_ln=False, ln=None):
+         want_ln=False, ln=None, want_colstats=False):
     assert a.dtype == BF and w.dtype == BF
     A = a.float() if a2 is None else torch.cat([a, a2], 1).float()
     h = A @ w.float().t()
@@ -130,7 +130,7 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
     return h
 
 
-def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None, residual=None, out_dtype=BF):
+def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None, residual=None, out_dtype=BF, want_colstats=False):
     assert x.dtype == BF and (sc_a is None or sc_a.dtype == BF) and (sc_b is None or sc_b.dtype == BF)
     B, H, W, Cin = x.shape
     w3 = w[:, : 9 * Cin].float().reshape(cout, 3, 3, Cin).permute(0, 3, 1, 2)
@@ -147,7 +147,7 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
     return y.to(out_dtype)
 
 
-def conv_up2x(x, w4, cout, bias=None):
+def conv_up2x(x, w4, cout, bias=None, want_colstats=False):
     """four parity 2x2 convs over the low-res map with the pre-summed bf16 weights, exactly as the kernel evaluates them"""
     assert x.dtype == BF and w4.dtype == BF
     B, H, W, Cin = x.shape

@@ -169,6 +169,50 @@ def test_gemm_geglu(M, C):
     assert rel(out, ref) < TOL
 
 
+@pytest.mark.parametrize("kind", ["gemm", "gemm_res", "conv", "conv_res", "up2x", "down"])
+def test_groupnorm_statistics_from_the_producer_epilogue(kind):
+    """the fp32-output epilogue emits per-tile column sums; GroupNorm built on them equals GroupNorm with its own pass."""
+    from instructany2pix_b200.packing import pack_conv3x3, pack_conv3x3_up2x
+    B, H, W, C = 2, 16, 16, 128                     # hw = 256 = two row tiles per image
+    if kind.startswith("gemm"):
+        a, w = rnd(B * H * W, 192), rnd(C, 192, scale=192 ** -0.5)
+        res = rnd(B * H * W, C, dtype=torch.float32) if kind == "gemm_res" else None
+        x = ops.gemm(a, w, bias=rnd(C, dtype=torch.float32), residual=res, out_dtype=torch.float32, want_colstats=True)
+        cs, segs = x._ia2p_cs
+        x4 = x.reshape(B, H, W, C)
+        x4._ia2p_cs = (cs, segs)
+    elif kind.startswith("conv"):
+        xi, w = rnd(B, H, W, 64), rnd(C, 64, 3, 3, scale=(9 * 64) ** -0.5)
+        res = rnd(B, H, W, C, dtype=torch.float32) if kind == "conv_res" else None
+        x4 = ops.conv3x3(xi, pack_conv3x3(w), C, bias=rnd(C, dtype=torch.float32), residual=res, out_dtype=torch.float32, want_colstats=True)
+        cs, segs = x4._ia2p_cs
+    elif kind == "up2x":
+        xi, w = rnd(B, H, W, 64), rnd(C, 64, 3, 3, scale=(9 * 64) ** -0.5)
+        x4 = ops.conv_up2x(xi, pack_conv3x3_up2x(w), C, bias=rnd(C, dtype=torch.float32), want_colstats=True)
+        cs, segs = x4._ia2p_cs
+        assert segs == 4
+    else:
+        xi, w = rnd(B, 2 * H, 2 * W, 64), rnd(C, 64, 3, 3, scale=(9 * 64) ** -0.5)
+        x4 = ops.conv3x3(xi, pack_conv3x3(w), C, stride=2, out_dtype=torch.float32, want_colstats=True)
+        cs, segs = x4._ia2p_cs
+    # the column sums themselves: every channel's total over all tiles equals the tensor's
+    assert rel(cs[..., 0].sum(0), x4.double().sum((0, 1, 2))) < 1e-5 and rel(cs[..., 1].sum(0), (x4.double() ** 2).sum((0, 1, 2))) < 1e-5
+    g, b = rnd(C, dtype=torch.float32) * 0.2 + 1.0, rnd(C, dtype=torch.float32) * 0.1
+    y_cs = ops.groupnorm(x4, None, g, b, 32, 1e-5, True)
+    plain = x4.clone()                                # a copy carries no statistics -> separate pass
+    y_own = ops.groupnorm(plain, None, g, b, 32, 1e-5, True)
+    ref = F.silu(F.group_norm(x4.permute(0, 3, 1, 2), 32, g, b, 1e-5)).permute(0, 2, 3, 1)
+    assert rel(y_cs, ref) < TOL and rel(y_own, ref) < TOL
+    assert (y_cs.float() - y_own.float()).abs().max() <= 2 ** -7 * ref.abs().max()      # same up to one bf16 ulp
+    # concat of two sources, both with statistics
+    if kind == "conv":
+        x5 = ops.conv3x3(rnd(B, H, W, 64, seed=9), pack_conv3x3(rnd(64, 64, 3, 3, scale=0.04, seed=10)), 64, out_dtype=torch.float32, want_colstats=True)
+        g2, b2 = rnd(C + 64, dtype=torch.float32) * 0.2 + 1.0, rnd(C + 64, dtype=torch.float32) * 0.1
+        y = ops.groupnorm(x4, x5, g2, b2, 32, 1e-5, False)
+        ref = F.group_norm(torch.cat([x4, x5], -1).permute(0, 3, 1, 2), 32, g2, b2, 1e-5).permute(0, 2, 3, 1)
+        assert rel(y, ref) < TOL
+
+
 def test_polar_interpolate_matches_reference_golden():
     """pipeline.py:295-300 run by oracle/gen_golden.py on the reference's own function (tests/golden/scalar_fns.npz), plus a
     full-size latent against the same formula in fp64."""
