@@ -171,6 +171,11 @@ int ia2p_conv_in_nchw(const void* x, int x_dtype, int64_t in_batch, int64_t B, i
 int ia2p_conv_out_nhwc(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin,
                        const float* w, const float* bias, void* out, int out_dtype, int64_t Cout, void* stream);
 
+/* out[b,c,p] = x[(b*HW + p)*ld + c] for c < C <= 8: the leading channels of an NHWC fp32 tensor as NCHW.  Second half of conv_out
+ * when it runs on the tensor cores (ia2p_conv3x3_nhwc_bf16 with the output channels zero-padded to 32): [3P] UNet conv_out
+ * (4 eps channels), VAE decoder conv_out (3) / encoder conv_out (8). */
+int ia2p_nhwc_prefix_to_nchw(const float* x, int64_t ld, float* out, int64_t B, int64_t HW, int64_t C, void* stream);
+
 /* 1x1 conv over <= 8 channels, NCHW fp32 -> NCHW fp32: out = scale * (w x) + bias.  Replaces [3P] AutoencoderKL.post_quant_conv
  * / quant_conv with the latent (un)scaling of ddim/sdxl_pipeline.py:866 and pnp_pipeline.py:204 folded into `scale`. */
 int ia2p_conv1x1_nchw_small(const float* x, const float* w, const float* bias, float* out, int64_t B, int64_t Cin,

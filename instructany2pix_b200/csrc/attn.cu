@@ -340,6 +340,10 @@ static int launch_cross(const void* q, int64_t ldq, const void* kt, const void* 
   int split = n_qtiles;
   for (int d = 1; d <= n_qtiles; ++d)
     if (n_qtiles % d == 0 && (long long)d * heads * batch >= 3LL * sm_count()) { split = d; break; }
+  if (const char* e = getenv("IA2P_XATTN_SPLIT")) {      // experiments only
+    const int v = atoi(e);
+    if (v >= 1 && v <= n_qtiles && n_qtiles % v == 0) split = v;
+  }
   const dim3 grid((unsigned)split, (unsigned)heads, (unsigned)batch);
   launch_pdl(cross_attn_kernel<T1, T2>, dim3(grid), dim3(256), smem, st, 
       static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(kt), static_cast<const __nv_bfloat16*>(vt),

@@ -1,5 +1,7 @@
 // HBM-bound elementwise kernels: fused CFG + DDIM update, inverse-DDIM axpby, prior CFG + DDPM step,
 // sinusoidal embeddings, nearest 2x upsample, conv_in / conv_out (few-channel 3x3 convs at the NCHW boundary).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ia2p {
@@ -183,40 +185,59 @@ conv_in_kernel(const TX* __restrict__ x, long long in_batch, long long B, int H,
   float* sw = sm;                       // [K][Cout]
   float* sp = sm + (size_t)K * Cout;    // [tile][K]
   const long long npix = B * (long long)H * W;
-  const long long pix0 = (long long)blockIdx.x * kConvInTile;
-  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {     // weights staged ONCE per CTA; the CTA then walks its pixel tiles
     const int co = i / K, k = i - co * K;              // w is [Cout][Cin][3][3] = [Cout][K]
     sw[k * Cout + co] = w[i];
   }
-  for (int i = threadIdx.x; i < kConvInTile * K; i += blockDim.x) {
-    const int p = i / K, k = i - p * K;
-    const int ci = k / 9, tap = k - ci * 9;
-    const long long pix = pix0 + p;
-    float v = 0.f;
-    if (pix < npix) {
-      const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
-      const long long b = pix / ((long long)W * H);
-      const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-        v = load_as_float(x + (((b % in_batch) * Cin + ci) * H + iy) * (long long)W + ix);
+  const long long ntiles = (npix + kConvInTile - 1) / kConvInTile;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long pix0 = tile * kConvInTile;
+    __syncthreads();                                   // previous tile's patch fully consumed (and weights visible)
+    for (int i = threadIdx.x; i < kConvInTile * K; i += blockDim.x) {
+      const int p = i / K, k = i - p * K;
+      const int ci = k / 9, tap = k - ci * 9;
+      const long long pix = pix0 + p;
+      float v = 0.f;
+      if (pix < npix) {
+        const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
+        const long long b = pix / ((long long)W * H);
+        const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          v = load_as_float(x + (((b % in_batch) * Cin + ci) * H + iy) * (long long)W + ix);
+      }
+      sp[i] = v;
     }
-    sp[i] = v;
-  }
-  __syncthreads();
-  const int cq_n = Cout / 4;
-  for (int idx = threadIdx.x; idx < kConvInTile * cq_n; idx += blockDim.x) {
-    const int p = idx / cq_n, cq = idx - p * cq_n;
-    const long long pix = pix0 + p;
-    if (pix >= npix) continue;
-    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* pp = sp + p * K;
-    for (int k = 0; k < K; ++k) {
-      const float v = pp[k];
-      const float4 wv = *reinterpret_cast<const float4*>(sw + k * Cout + cq * 4);
-      acc.x += v * wv.x; acc.y += v * wv.y; acc.z += v * wv.z; acc.w += v * wv.w;
+    __syncthreads();
+    // register tile: 4 pixels (p, p+16, p+32, p+48) x 4 output channels per thread, so one 16-byte weight read feeds 16 FMAs
+    // (the one-pixel version was bound by shared-memory bandwidth: 5 wavefronts per 4 FMAs)
+    const int cq_n = Cout / 4;
+    for (int idx = threadIdx.x; idx < (kConvInTile / 4) * cq_n; idx += blockDim.x) {
+      const int pg = idx / cq_n, cq = idx - pg * cq_n;
+      const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc[4] = {b4, b4, b4, b4};
+      const float* pp = sp + pg * K;
+      for (int k = 0; k < K; ++k) {
+        const float4 wv = *reinterpret_cast<const float4*>(sw + k * Cout + cq * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v = pp[j * (kConvInTile / 4) * K + k];
+          acc[j].x += v * wv.x; acc[j].y += v * wv.y; acc[j].z += v * wv.z; acc[j].w += v * wv.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long pix = pix0 + pg + j * (kConvInTile / 4);
+        if (pix >= npix) continue;
+        TO* o = out + pix * Cout + cq * 4;
+        if constexpr (sizeof(TO) == 4) {
+          *reinterpret_cast<float4*>(o) = acc[j];                                  // one 16-byte store per thread, coalesced
+        } else if constexpr (sizeof(TO) == 2 && std::is_same<TO, __nv_bfloat16>::value) {
+          *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(acc[j].x, acc[j].y), pack_bf16x2(acc[j].z, acc[j].w));
+        } else {
+          store_from_float(o, acc[j].x); store_from_float(o + 1, acc[j].y); store_from_float(o + 2, acc[j].z); store_from_float(o + 3, acc[j].w);
+        }
+      }
     }
-    TO* o = out + pix * Cout + cq * 4;
-    store_from_float(o, acc.x); store_from_float(o + 1, acc.y); store_from_float(o + 2, acc.z); store_from_float(o + 3, acc.w);
   }
 }
 
@@ -297,6 +318,25 @@ __global__ void gaussian_sample_kernel(const float* __restrict__ moments, const 
     float v = mean;
     if (noise != nullptr) v += expf(0.5f * fminf(fmaxf(moments[b * 2 * CHW + CHW + r], -30.f), 20.f)) * noise[i];
     out[i] = v * scale;
+  }
+}
+
+// out[b, c, p] = x[(b * hw + p) * ld + c], c < C <= 8: the first C channels of an NHWC fp32 tensor as NCHW.  Used after a
+// few-output-channel 3x3 conv that ran on the tensor cores with its output channels zero-padded to 32 (conv_out of the UNet /
+// VAE): thread = pixel, reads one 16/32-byte prefix of its row, writes C plane elements (coalesced per plane).
+__global__ void nhwc_prefix_to_nchw_kernel(const float* __restrict__ x, long long ld, float* __restrict__ out, long long B, long long hw,
+                                           int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * hw; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, p = i - b * hw;
+    const float4 v0 = *reinterpret_cast<const float4*>(x + i * ld);
+    float v[8] = {v0.x, v0.y, v0.z, v0.w, 0.f, 0.f, 0.f, 0.f};
+    if (C > 4) {
+      const float4 v1 = *reinterpret_cast<const float4*>(x + i * ld + 4);
+      v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+    }
+    for (int c = 0; c < C; ++c) out[(b * C + c) * hw + p] = v[c];
   }
 }
 
@@ -475,8 +515,10 @@ extern "C" int ia2p_conv_in_nchw(const void* x, int x_dtype, int64_t in_batch, i
   IA2P_REQUIRE(Cin >= 1 && Cin <= 8 && Cout % 8 == 0 && Cout <= 640, IA2P_E_SHAPE, "conv_in: Cin<=8, Cout%%8==0, Cout<=640 required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long npix = B * H * W;
-  const unsigned grid = (unsigned)((npix + kConvInTile - 1) / kConvInTile);
   const size_t smem = (size_t)Cin * 9 * (Cout + kConvInTile) * sizeof(float);
+  const long long ntiles = (npix + kConvInTile - 1) / kConvInTile;
+  const long long resident = (long long)sm_count() * (smem <= 56 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1));
+  const unsigned grid = (unsigned)(ntiles < resident ? ntiles : resident);      // persistent: weights are staged once per CTA
   IA2P_REQUIRE(smem <= 200 * 1024, IA2P_E_SHAPE, "conv_in: shared-memory footprint too large");
 #define IA2P_CONV_IN(TX_, TO_)                                                                                           \
   do {                                                                                                                   \
@@ -522,6 +564,16 @@ extern "C" int ia2p_conv1x1_nchw_small(const float* x, const float* w, const flo
   IA2P_REQUIRE(Cin >= 1 && Cin <= 8 && Cout >= 1 && Cout <= 8, IA2P_E_SHAPE, "conv1x1_nchw_small: channel counts must be in [1, 8]");
   IA2P_CUDA(launch_pdl(conv1x1_nchw_small_kernel, dim3(grid_for(B * HW, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, w, bias, out,
                        (long long)B, (int)Cin, (int)Cout, (long long)HW, scale));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_nhwc_prefix_to_nchw(const float* x, int64_t ld, float* out, int64_t B, int64_t HW, int64_t C, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(x && out && B > 0 && HW > 0 && C >= 1 && C <= 8, IA2P_E_ARG, "nhwc_prefix_to_nchw: bad arguments");
+  IA2P_REQUIRE(ld % 4 == 0 && ld >= 8 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, IA2P_E_ALIGN, "nhwc_prefix_to_nchw: ld %% 4 == 0, ld >= 8, 16-byte base");
+  IA2P_CUDA(launch_pdl(nhwc_prefix_to_nchw_kernel, dim3(grid_for(B * HW, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, (long long)ld,
+                       out, (long long)B, (long long)HW, (int)C));
   IA2P_LAUNCH_CHECK();
   return 0;
 }

@@ -429,6 +429,17 @@ def conv_out(x, w, bias, out_dtype=torch.float32):
     return out
 
 
+def conv_out_tc(x, w32, b32, cout):
+    """conv_out on the tensor cores: 3x3 conv with the ``cout`` (<= 8) output channels zero-padded to 32 (``w32`` [32, 9*Cin]
+    bf16, ``b32`` [32] fp32; packing.pack_conv_out) followed by the NHWC-prefix -> NCHW copy.  x NHWC bf16 -> [B, cout, H, W] fp32."""
+    lib = _lib.load()
+    B, H, W, _ = x.shape
+    y = conv3x3(x, w32, 32, bias=b32, out_dtype=torch.float32)
+    out = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
+    _run(lib.ia2p_nhwc_prefix_to_nchw, (y.data_ptr(), 32, out.data_ptr(), B, H * W, cout, _stream()), "nhwc_prefix_to_nchw")
+    return out
+
+
 def conv1x1_nchw_small(x, w, bias, scale=1.0):
     """1x1 conv over <= 8 channels, NCHW fp32 -> NCHW fp32: scale * (w x) + bias (VAE post_quant_conv / quant_conv)."""
     lib = _lib.load()

@@ -40,6 +40,18 @@ def pack_conv3x3_up2x(w, dtype=torch.bfloat16):
     return torch.stack(out, 0).to(dtype).contiguous()
 
 
+def pack_conv_out(w, b, pad_to=32, dtype=torch.bfloat16):
+    """few-output-channel Conv2d [cout <= 8, Cin, 3, 3] -> ([pad_to, 9*Cin] bf16 with zero rows, [pad_to] fp32 bias): conv_out as a
+    tensor-core conv whose extra output channels are discarded (ops.conv_out_tc)."""
+    cout = w.shape[0]
+    wp = torch.zeros(pad_to, w.shape[1] * 9, device=w.device, dtype=dtype)
+    wp[:cout] = pack_conv3x3(w, dtype=dtype)
+    bp = torch.zeros(pad_to, device=w.device, dtype=torch.float32)
+    if b is not None:
+        bp[:cout] = b.detach().float()
+    return wp.contiguous(), bp
+
+
 def interleave_geglu(w, b=None, group=32):
     """GEGLU proj weight [8C, C] (rows [0,4C) value | [4C,8C) gate) -> rows interleaved in `group`-row
     blocks [value_0 | gate_0 | value_1 | gate_1 ...] so value/gate of one output land in the same accumulator tile."""

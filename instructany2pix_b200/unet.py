@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from . import ops
 from .attention_processor import B200AttnProcessor, B200IPAttnProcessor, is_ip_processor, is_plain_processor
-from .packing import interleave_geglu, pack_conv3x3, pack_conv3x3_up2x
+from .packing import interleave_geglu, pack_conv3x3, pack_conv3x3_up2x, pack_conv_out
 
 
 @dataclass
@@ -366,6 +366,7 @@ class B200UNet(nn.Module):
                     P[name]["w4"] = pack_conv3x3_up2x(m.conv.weight)
         P["conv_in"] = (f32(self.conv_in.weight), f32(self.conv_in.bias))
         P["conv_out"] = (f32(self.conv_out.weight.permute(0, 2, 3, 1)), f32(self.conv_out.bias))
+        P["conv_out_tc"] = pack_conv_out(self.conv_out.weight, self.conv_out.bias)       # tensor-core form (output channels padded to 32)
         P["norm_out"] = (f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias))
         P["time"] = (bf(self.time_embedding.linear_1.weight), f32(self.time_embedding.linear_1.bias),
                      bf(self.time_embedding.linear_2.weight), f32(self.time_embedding.linear_2.bias))
@@ -613,5 +614,7 @@ class B200UNet(nn.Module):
                     x = ops.conv3x3(ops.upsample2x(x), p["w"], p["w"].shape[0], bias=p["b"], out_dtype=SD)
         g, b = P["norm_out"]
         x = ops.groupnorm(x, None, g, b, G, cfg.norm_eps, True)
+        if out_dtype == torch.float32 and x.shape[-1] % 64 == 0:
+            return ops.conv_out_tc(x, *P["conv_out_tc"], cfg.out_channels)
         w_out, b_out = P["conv_out"]
         return ops.conv_out(x, w_out, b_out, out_dtype=out_dtype)

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .packing import pack_conv3x3, pack_conv3x3_up2x
+from .packing import pack_conv3x3, pack_conv3x3_up2x, pack_conv_out
 
 
 @dataclass
@@ -182,7 +182,7 @@ class B200VAE(nn.Module):
             if hasattr(self, side):
                 mod = getattr(self, side)
                 P[side + ".conv_in"] = (f32(mod.conv_in.weight), f32(mod.conv_in.bias))
-                P[side + ".conv_out"] = (f32(mod.conv_out.weight.permute(0, 2, 3, 1)), f32(mod.conv_out.bias))
+                P[side + ".conv_out"] = pack_conv_out(mod.conv_out.weight, mod.conv_out.bias)
                 P[side + ".norm_out"] = (f32(mod.conv_norm_out.weight), f32(mod.conv_norm_out.bias))
         self._packed = P
         return P
@@ -244,7 +244,7 @@ class B200VAE(nn.Module):
                 q = P[f"decoder.up_blocks.{i}.upsamplers.0"]
                 x = ops.conv_up2x(ops.to_bf16(x), q["w4"], q["w"].shape[0], bias=q["b"], want_colstats=True)   # Upsample2D folded
         h = ops.groupnorm(x, None, *P["decoder.norm_out"], G, 1e-6, True)
-        return ops.conv_out(h, *P["decoder.conv_out"], out_dtype=torch.float32)
+        return ops.conv_out_tc(h, *P["decoder.conv_out"], cfg.out_channels)
 
     # ------------------------------------------------------------------ encode (pnp_pipeline.py:195-204)
     @torch.no_grad()
@@ -262,7 +262,7 @@ class B200VAE(nn.Module):
                 x = ops.conv3x3_down_padend(ops.to_bf16(x), q["w"], q["w"].shape[0], bias=q["b"], out_dtype=torch.float32)
         x = self._mid(P, "encoder", x)
         h = ops.groupnorm(x, None, *P["encoder.norm_out"], G, 1e-6, True)
-        moments = ops.conv_out(h, *P["encoder.conv_out"], out_dtype=torch.float32)                  # (B, 8, h, w)
+        moments = ops.conv_out_tc(h, *P["encoder.conv_out"], 2 * cfg.latent_channels)               # (B, 8, h, w)
         moments = ops.conv1x1_nchw_small(moments, self.quant_conv.weight, self.quant_conv.bias, 1.0)
         sf = cfg.scaling_factor if scaled else 1.0
         if not sample:

@@ -164,6 +164,11 @@ def conv_up2x(x, w4, cout, bias=None, want_colstats=False):
     return out
 
 
+def conv_out_tc(x, w32, b32, cout):
+    y = conv3x3(x, w32, 32, bias=b32, out_dtype=torch.float32)
+    return y[..., :cout].permute(0, 3, 1, 2).contiguous()
+
+
 def conv_in(x_nchw, w, bias, out_batch=None, out_dtype=BF):
     B = out_batch or x_nchw.shape[0]
     x = x_nchw.float().repeat(B // x_nchw.shape[0], 1, 1, 1)
