@@ -55,6 +55,37 @@ def test_forward_parity_deep_narrow():
     assert e < EPS_TOL
 
 
+def test_forward_parity_sdxl_width():
+    """the real SDXL-base configuration (2 567 463 684 parameters + 70 IP processors, name-seeded synthetic weights) at a 32x32
+    latent (256^2 image), CFG pair: one teacher-forced forward against the fp32 CPU oracle.  ~2 min (weight synthesis dominates)."""
+    from oracle.attention import IPAttnProcessor2_0
+    from oracle.synth import synth_input, synth_state_dict
+    from oracle.unet import SDXL_BASE, OracleUNet
+    o = OracleUNet(SDXL_BASE).eval()
+    o.load_state_dict(synth_state_dict(o, 0))
+    procs = {}
+    for name, p in o.attn_processors.items():
+        if name.endswith("attn2.processor"):
+            C = dict(o.named_modules())[name[: -len(".processor")]].to_q.weight.shape[0]
+            ip = IPAttnProcessor2_0(C, SDXL_BASE.cross_attention_dim, scale=1.0, num_tokens=4)
+            ip.load_state_dict(synth_state_dict({name + "." + k: v.shape for k, v in ip.state_dict().items()}, 5), strict=False)
+            for k, v in ip.state_dict().items():
+                v.copy_(synth_state_dict({name + k: v.shape}, 5)[name + k])
+            procs[name] = ip
+        else:
+            procs[name] = p
+    o.set_attn_processor(procs)
+    b = B200UNet.from_module(o, device="cuda")
+    x = synth_input("full/x", (2, 4, 32, 32))
+    ctx = synth_input("full/ctx", (2, 81, 2048))
+    added = dict(text_embeds=synth_input("full/pooled", (2, 1280)), time_ids=torch.tensor([[256.0, 256.0, 0.0, 0.0, 256.0, 256.0]] * 2))
+    ref = o(x, torch.tensor(601), ctx, added_cond_kwargs=added)[0]
+    out = b(cu(x), 601, cu(ctx), added_cond_kwargs=cu(added))[0]
+    e = rel(out.cpu(), ref)
+    print(f"SDXL-width forward (2.57 B parameters): eps rel-L2 = {e:.2e}")
+    assert e < EPS_TOL
+
+
 def test_forward_parity_refiner_topology():
     """SDXL-refiner block layout (4 levels, attention on the middle two, 4 layers per block, plain text-only cross-attention,
     five micro-conditioning ids) at narrow width: the same kernels with a different shape table."""
