@@ -99,3 +99,34 @@ def test_softmax_rows_conv1x1_gaussian_sample():
     mean, logvar = m.chunk(2, 1)
     assert rel(ops.gaussian_sample(m, nz, 0.13025), (mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * nz) * 0.13025) < 1e-6
     assert torch.equal(ops.gaussian_sample(m, None, 1.0), mean.contiguous())
+
+
+def test_edit_chain_matches_the_oracle_chain():
+    """encode -> DDIM inversion -> polar start latent -> CFG sampling -> decode (pipeline.py:303-361 after the encoders), B200
+    path vs the same chain on the fp32 oracles with identical weights and noise draws: image PSNR >= 35 dB."""
+    from instructany2pix_b200.hotpath import B200HotPath
+    from oracle import sampler as osampler
+    from oracle.schedulers import polar_interpolate
+    from oracle.unet import TINY
+    from tests.test_host_unet_emu import build_pair, make_inputs
+    dec, enc, vae = build(SMALL)
+    o, b = build_pair(True, device="cuda")
+    lat, ctx, added = make_inputs(TINY, B=1, L=16)
+    img = synth_input("chain/img", (1, 3, 128, 128), seed=1).clamp(-1, 1)
+    n_enc, n_pol = synth_input("chain/enc", (1, 4, 16, 16), seed=2), synth_input("chain/pol", (1, 4, 16, 16), seed=3)
+    ctx_inv, added_inv = ctx[1:, :77], {k: v[1:] for k, v in added.items()}
+    # oracle chain
+    z0 = enc.encode(img, n_enc)
+    z_inv = osampler.invert(o, z0, ctx_inv, added_inv, num_inference_steps=4)
+    z_t = polar_interpolate(z_inv, n_pol, 0.7)
+    z = osampler.generate(o, z_t, ctx, added, num_inference_steps=4, guidance_scale=7.5)
+    ref = dec.decode(z)
+    # B200 chain
+    cu = lambda t: {k: v.cuda() for k, v in t.items()} if isinstance(t, dict) else t.cuda()
+    hp = B200HotPath(b, vae)
+    out, zb = hp.edit(img.cuda(), cu(ctx_inv), cu(added_inv), cu(ctx), cu(added), alpha=0.7, num_inference_steps=4, guidance_scale=7.5,
+                      noise=n_pol.cuda(), encode_noise=n_enc.cuda(), return_latents=True)
+    s = ref.abs().max().clamp_min(1e-6)
+    db = psnr(out.cpu() / s, ref / s)
+    print(f"edit chain: final latent rel-L2 {rel(zb, z):.2e}, image PSNR {db:.1f} dB")
+    assert db >= 35.0
