@@ -119,6 +119,12 @@ int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64
  * statistics pass over it.  Tiles follow the output pixel order (128 consecutive pixels; needs H*W % 128 == 0 to be usable by
  * GroupNorm); conv_up2x writes 4 segments, one per output parity. */
 
+/* One-shot hint for the NEXT ia2p_gemm_* / ia2p_conv* call made by this host thread: that launch also pulls `bytes` of
+ * `next_weights` (the weight matrix of the tensor-core launch that will follow it) into L2, so the following kernel's first
+ * wave does not start on cold DRAM misses (each layer's weights are touched once per step and never survive in L2).  The
+ * pointer is only read by the kernel that consumes the hint; pass NULL / 0 to clear.  Purely a performance hint. */
+int ia2p_tc_prefetch_hint(const void* next_weights, int64_t bytes);
+
 /* first dimension of a conv's `colstats` buffer for a [B, Ho, Wo] output grid (conv_up2x: per parity segment, on its input
  * grid), or 0 when a 128-pixel tile would span several images and the statistics must not be requested; GEMMs: ceil(M / 128). */
 int64_t ia2p_conv_colstats_tiles(int64_t B, int64_t Ho, int64_t Wo);

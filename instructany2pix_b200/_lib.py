@@ -38,6 +38,7 @@ SIGNATURES = {
                            _p, _l, _p, _p, _p, _l, _p, _f, _p], _i),
     "ia2p_gemm_ln_parts": ([_l, _l], _l),
     "ia2p_conv_colstats_tiles": ([_l, _l, _l], _l),
+    "ia2p_tc_prefetch_hint": ([_p, _l], _i),
     "ia2p_conv3x3_nhwc_bf16": ([_p, _l, _l, _l, _l, _i, _p, _p, _l, _p, _l, _p, _i, _l, _p, _p, _p, _i, _p, _p], _i),
     "ia2p_conv_up2x_nhwc_bf16": ([_p, _l, _l, _l, _l, _p, _p, _l, _p, _p, _p], _i),
     "ia2p_conv3x3_s2_padend_nhwc_bf16": ([_p, _l, _l, _l, _l, _p, _p, _i, _l, _p, _p], _i),

@@ -252,6 +252,11 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// L2 prefetch of a contiguous global range (no shared memory involved, no completion to wait for); bytes % 16 == 0
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // CTA-pair (cta_group::2) loads: data lands in THIS CTA's smem, the completion is signalled on the LEADER CTA's mbarrier
 // (same smem offset, peer bit cleared -- the addressing CUTLASS's SM100_TMA_2SM_LOAD uses).
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;

@@ -42,6 +42,10 @@ struct TcParams {
   // ones that would form a last, mostly idle wave -- are cut into `split` column slices each, so that every SM gets a slice.
   int full_items, total_items, split;
   int trace_id;                    // debug build: launch id for the in-graph timeline
+  // Weight prefetch hint (ia2p_tc_prefetch_hint): the NEXT tcgen05 launch's weight matrix.  Every CTA pulls its slice into L2
+  // once its first tile's loads are under way, so the next kernel's first wave does not start on cold DRAM misses.
+  const char* pf_ptr;
+  long long pf_bytes;
   int Wo, Ho, B;                   // output pixel grid (plain GEMM: Wo = M, Ho = B = 1)
   int N;                           // GEMM N (pre-GEGLU)
   int rows_per_batch;              // rowbias row = pixel / rows_per_batch
@@ -192,6 +196,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     int stage = 0;
     uint32_t phase = 0;
     TRACE_DECL(tr_wait_empty);
+    bool pf_done = (p.pf_ptr == nullptr);
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
       const int m_tile = ti.m_unit * CG + (int)rank;    // may be == m_tiles for the odd tail: TMA zero-fills (batch coord OOB)
@@ -227,6 +232,19 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (!pf_done) {                                   // first tile's loads issued: now pull this CTA's slice of the next weights
+        pf_done = true;
+        if (lane == 0) {
+          const long long per = ((p.pf_bytes / (long long)gridDim.x + 4095) / 4096) * 4096;
+          const long long lo = per * (long long)blockIdx.x;
+          long long hi = lo + per;
+          if (hi > p.pf_bytes) hi = p.pf_bytes;
+          for (long long o = lo; o < hi; o += 16384) {
+            const long long n = (hi - o < 16384) ? ((hi - o) & ~15LL) : 16384;
+            if (n > 0) bulk_prefetch_l2(p.pf_ptr + o, (uint32_t)n);
+          }
         }
       }
     }
@@ -827,6 +845,9 @@ static int pick_block_n(int64_t N, bool geglu, int64_t m_tiles) {
   return last != 0 ? last : 128;                         // 128 with a ragged last tile when nothing divides N
 }
 
+static thread_local const void* g_pf_ptr = nullptr;
+static thread_local long long g_pf_bytes = 0;
+
 static bool tail_split_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -879,6 +900,10 @@ static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
 #ifdef IA2P_TC_TRACE
   p.trace_id = g_tc_launch_id++;
 #endif
+  p.pf_ptr = static_cast<const char*>(g_pf_ptr);       // one-shot hint: consumed by this launch
+  p.pf_bytes = g_pf_bytes;
+  g_pf_ptr = nullptr;
+  g_pf_bytes = 0;
   IA2P_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG, EPI>, maps, p));
   IA2P_LAUNCH_CHECK();
   return 0;
@@ -995,6 +1020,12 @@ extern "C" int ia2p_debug_set_trace(void* dev_buffer) {       // debug build onl
   return (int)cudaMemcpyToSymbol(g_tc_trace, &p, sizeof(p));
 }
 #endif
+
+extern "C" int ia2p_tc_prefetch_hint(const void* next_weights, int64_t bytes) {
+  g_pf_ptr = (bytes >= 16 && (reinterpret_cast<uintptr_t>(next_weights) & 15) == 0) ? next_weights : nullptr;
+  g_pf_bytes = g_pf_ptr ? (bytes & ~15LL) : 0;
+  return 0;
+}
 
 extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                               const void* W, void* out, int64_t ldo, int64_t M, int64_t N,

@@ -246,6 +246,7 @@ class B200UNet(nn.Module):
         self._kv_cache = {}
         self._temb_cache = {}
         self._proc_version = 0
+        self._wplans = {}
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -278,6 +279,7 @@ class B200UNet(nn.Module):
         self._packed = None
         self._kv_cache.clear()
         self._temb_cache.clear()
+        self._wplans.clear()
 
     @property
     def dtype(self):
@@ -506,6 +508,20 @@ class B200UNet(nn.Module):
         """All per-step device work (capturable in a CUDA graph: no host sync, no data-dependent control flow).
         ``sample`` may hold ``batch`` or ``batch // 2`` images (CFG duplication is folded into conv_in)."""
         P = self.prepare()
+        cfg = self.config
+        G = cfg.norm_num_groups
+        kv_t, kv_i, n_text, n_ip = kv
+        _, ip_scale = self._ip_state()
+        # weight prefetch plan: keyed by everything that fixes the launch order (packed weights, batch, resolution, processors)
+        pkey = (id(P), batch, tuple(sample.shape[-2:]), n_text, n_ip, self._proc_version)
+        plan = self._wplans.setdefault(pkey, {"seq": [], "ready": False})
+        ops.plan_begin(plan)
+        try:
+            return self._forward_core(sample, rowbias, kv, batch, out_dtype, P)
+        finally:
+            ops.plan_end()
+
+    def _forward_core(self, sample, rowbias, kv, batch, out_dtype, P):
         cfg = self.config
         G = cfg.norm_num_groups
         kv_t, kv_i, n_text, n_ip = kv
