@@ -55,6 +55,20 @@ def test_forward_parity_deep_narrow():
     assert e < EPS_TOL
 
 
+@pytest.mark.parametrize("B,L", [(3, 24), (1, 40), (5, 8)])
+def test_forward_parity_ragged_shapes(B, L):
+    """odd batch sizes and latent sides that are not powers of two (24 -> 576 / 144 / 36 tokens per level: ragged row tiles,
+    tiles spanning several images, ragged attention key blocks), sampler path with CFG duplication folded into conv_in."""
+    o, b = build_pair(True, device="cuda")
+    lat, ctx, added = make_inputs(TINY, B=B, L=L)
+    x = torch.cat([lat, lat])
+    ref = o(x, torch.tensor(321), ctx, added_cond_kwargs=added)[0]
+    out = b(cu(x), 321, cu(ctx), added_cond_kwargs=cu(added))[0]
+    e = rel(out.cpu(), ref)
+    print(f"ragged forward B={B} L={L}: eps rel-L2 = {e:.2e}")
+    assert out.shape == ref.shape and e < EPS_TOL
+
+
 def test_forward_parity_sdxl_width():
     """the real SDXL-base configuration (2 567 463 684 parameters + 70 IP processors, name-seeded synthetic weights) at a 32x32
     latent (256^2 image), CFG pair: one teacher-forced forward against the fp32 CPU oracle.  ~2 min (weight synthesis dominates)."""
