@@ -48,6 +48,13 @@ int ia2p_cfg_ddim_step(const void* eps2, int eps_dtype, const void* x, void* x_o
 int ia2p_axpby(const void* eps, int eps_dtype, const void* x, void* x_out, int x_dtype, int64_t n,
                float c_x, float c_e, void* stream);
 
+/* Inpainting loop tail: out = (1 - mask) * (c_x * orig + c_e * noise) + mask * latents, fp32, mask [B,1,HW] broadcast over C.
+ * Replaces `latents = (1 - init_mask) * scheduler.add_noise(image_latents, noise, t_next) + init_mask * latents` of the [3P]
+ * StableDiffusionXLInpaintPipeline loop the reference reaches through gdino/lib.py:85-102 (subject_consistency, pipeline.py:366);
+ * (c_x, c_e) = add_noise coefficients of the next timestep (DDIM: sqrt(a), sqrt(1-a); Euler: 1, sigma); noise NULL on the last step. */
+int ia2p_inpaint_blend(const float* latents, const float* orig_latents, const float* noise, const float* mask, float* out,
+                       int64_t B, int64_t C, int64_t HW, float c_x, float c_e, void* stream);
+
 /* Start-latent blend: out = ll/|ll| * (alpha|x| + (1-alpha)|y|), ll = alpha x + (1-alpha) y, norms over all n elements, fp32.
  * Replaces InstructAny2PixPipeline.polar_intrtpolate, pipeline.py:295-300 (call site :332-336: inverted latent vs fresh noise).
  * workspace: ia2p_polar_workspace_bytes() bytes of device memory (per-block partial sums; bit-reproducible, no atomics). */

@@ -24,6 +24,7 @@ SIGNATURES = {
     "ia2p_device_check": ([_i], _i),
     "ia2p_cfg_ddim_step": ([_p, _i, _p, _p, _i, _p, _i, _l, _l, _f, _f, _f, _p], _i),
     "ia2p_axpby": ([_p, _i, _p, _p, _i, _l, _f, _f, _p], _i),
+    "ia2p_inpaint_blend": ([_p, _p, _p, _p, _p, _l, _l, _l, _f, _f, _p], _i),
     "ia2p_polar_workspace_bytes": ([], _l),
     "ia2p_polar_interpolate": ([_p, _p, _p, _l, _f, _p, _p], _i),
     "ia2p_prior_cfg_ddpm_step": ([_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _p], _i),

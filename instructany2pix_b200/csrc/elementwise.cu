@@ -55,6 +55,23 @@ __global__ void prior_step_kernel(const float* __restrict__ x0_pair, const float
   }
 }
 
+// ---------------------------------------------------------------- inpainting blend ([3P] StableDiffusionXLInpaintPipeline loop tail)
+// out = (1 - m) * (c_x * x0 + c_e * noise) + m * lat: the known region is reset to the (re-noised) original latents after every
+// step; m: [B, 1, hw] broadcast over the C channels.  noise may be NULL (last step: the clean original).
+__global__ void inpaint_blend_kernel(const float* __restrict__ lat, const float* __restrict__ x0, const float* __restrict__ noise,
+                                     const float* __restrict__ mask, float* __restrict__ out, long long B, int C, long long hw,
+                                     float c_x, float c_e) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * C * hw; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / (C * hw), p = i % hw;
+    const float m = mask[b * hw + p];
+    float keep = c_x * x0[i];
+    if (noise != nullptr) keep += c_e * noise[i];
+    out[i] = (1.f - m) * keep + m * lat[i];
+  }
+}
+
 // ---------------------------------------------------------------- polar interpolation of two latents (pipeline.py:295-300)
 // out = ll / |ll| * (alpha |x| + (1 - alpha) |y|),  ll = alpha x + (1 - alpha) y;  norms over the WHOLE tensor.
 // Pass 1: per-block partial sums of x^2, y^2, ll^2 (fp64, fixed order -> bit-reproducible); pass 2: every block re-reduces the
@@ -441,6 +458,16 @@ extern "C" int ia2p_axpby(const void* eps, int eps_dtype, const void* x, void* x
   DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX,
       (launch_pdl(axpby_kernel<TE, TX>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps), static_cast<const TX*>(x),
                                                   static_cast<TX*>(x_out), n, c_x, c_e))));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ia2p_inpaint_blend(const float* latents, const float* orig_latents, const float* noise, const float* mask, float* out,
+                                  int64_t B, int64_t C, int64_t HW, float c_x, float c_e, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(latents && orig_latents && mask && out && B > 0 && C > 0 && HW > 0, IA2P_E_ARG, "inpaint_blend: bad arguments");
+  IA2P_CUDA(launch_pdl(inpaint_blend_kernel, dim3(grid_for(B * C * HW, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), latents,
+                       orig_latents, noise, mask, out, (long long)B, (int)C, (long long)HW, c_x, c_e));
   IA2P_LAUNCH_CHECK();
   return 0;
 }

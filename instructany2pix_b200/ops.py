@@ -156,6 +156,20 @@ def axpby(eps, x, c_x, c_e, out=None):
     return out
 
 
+def inpaint_blend(latents, orig, noise, mask, c_x, c_e, out=None):
+    """out = (1 - mask) * (c_x * orig + c_e * noise) + mask * latents (inpainting loop tail); mask (B,1,H,W), noise may be None."""
+    lib = _lib.load()
+    latents, orig, mask = _f32(latents, "latents"), _f32(orig, "orig"), _f32(mask, "mask")
+    noise = None if noise is None else _f32(noise, "noise")
+    B, C, H, W = latents.shape
+    assert orig.shape == latents.shape and mask.shape == (B, 1, H, W)
+    if out is None:
+        out = torch.empty_like(latents)
+    _run(lib.ia2p_inpaint_blend, (latents.data_ptr(), orig.data_ptr(), _ptr(noise), mask.data_ptr(), out.data_ptr(), B, C, H * W,
+                                      float(c_x), float(c_e), _stream()), "inpaint_blend")
+    return out
+
+
 def polar_interpolate(x, y, alpha, out=None):
     """``InstructAny2PixPipeline.polar_intrtpolate`` (pipeline.py:295-300): blend two latents and restore the blended norm;
     norms are taken over the whole tensor, fp32."""

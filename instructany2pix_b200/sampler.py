@@ -82,19 +82,40 @@ class B200Sampler:
     # ------------------------------------------------------------------ generation (CFG, DDIM eta=0)
     @torch.no_grad()
     def generate(self, latents, ctx, added_cond_kwargs, num_inference_steps=50, guidance_scale=10.0, trace=None,
-                 teacher=None):
+                 teacher=None, init_latents=None, strength=1.0, inpaint_mask=None):
         """latents: (B,4,L,L) initial noise; ctx: (2B,S,D) = cat([negative, positive]) incl. IP tokens
         (ip_adapter.py:341-342, custom_pipelines.py:296-302); added_cond_kwargs: text_embeds (2B,P), time_ids (2B,6).
-        Returns final latents (B,4,L,L) fp32 on the device."""
+        Returns final latents (B,4,L,L) fp32 on the device.
+
+        img2img / refiner (pipeline.py:358-361, [3P] StableDiffusionXLImg2ImgPipeline): ``init_latents`` (the encoded image) and
+        ``strength`` < 1 -> only the last int(N * strength) steps run, starting from ``add_noise(init_latents, latents, t_start)``.
+        Inpainting (gdino/lib.py:85-102, [3P] StableDiffusionXLInpaintPipeline with a 4-channel UNet): additionally
+        ``inpaint_mask`` (B,1,L,L), 1 = repaint: after every step the kept region is reset to the re-noised original."""
         s = self.scheduler
         s.set_timesteps(num_inference_steps)
         B = latents.shape[0]
         assert ctx.shape[0] == 2 * B, "ctx must hold [uncond; cond] rows"
-        ent, table, n_text, n_ip = self._prepare("gen", latents, ctx, added_cond_kwargs, 2 * B, s.timesteps)
+        timesteps = s.timesteps
+        if init_latents is not None:
+            n_run = min(int(num_inference_steps * strength), num_inference_steps)
+            timesteps = timesteps[max(num_inference_steps - n_run, 0):]
+            assert len(timesteps) > 0, "strength too small: no denoising step left"
+        ent, table, n_text, n_ip = self._prepare("gen", latents, ctx, added_cond_kwargs, 2 * B, timesteps)
         scaled_input = hasattr(s, "input_scale")           # Euler: the UNet sees x / sqrt(sigma^2 + 1), DDIM: x itself
         x = torch.empty_like(ent["x"]) if scaled_input else ent["x"]
-        x.copy_(latents.to(torch.float32) * s.init_noise_sigma)
-        for i, t in enumerate(s.timesteps.tolist()):
+        noise = latents.to(x.device, torch.float32)
+        if init_latents is None:
+            x.copy_(noise * s.init_noise_sigma)
+        else:
+            orig = init_latents.to(x.device, torch.float32).contiguous()
+            if strength >= 1.0 and inpaint_mask is not None:
+                x.copy_(noise * s.init_noise_sigma)            # pure-noise start ([3P] inpaint pipeline, strength == 1)
+            else:
+                c_x, c_e = s.add_noise_coefficients(timesteps[0])
+                ops.axpby(noise.contiguous(), orig, c_x, c_e, out=x)
+        mask = None if inpaint_mask is None else inpaint_mask.to(x.device, torch.float32).contiguous()
+        ts_list = timesteps.tolist()
+        for i, t in enumerate(ts_list):
             if teacher is not None:
                 x.copy_(teacher[i])
             if scaled_input:
@@ -104,6 +125,12 @@ class B200Sampler:
             if trace is not None:
                 trace.append(dict(t=t, x=x.clone(), eps2=ent["eps"].clone()))
             s.cfg_step(ent["eps"], t, x, guidance_scale, out=x)
+            if mask is not None:
+                if i + 1 < len(ts_list):
+                    c_x, c_e = s.add_noise_coefficients(ts_list[i + 1])
+                    ops.inpaint_blend(x, orig, noise, mask, c_x, c_e, out=x)
+                else:
+                    ops.inpaint_blend(x, orig, None, mask, 1.0, 0.0, out=x)
         return x.clone()
 
     # ------------------------------------------------------------------ DDIM inversion (batch B, no CFG)

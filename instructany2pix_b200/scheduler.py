@@ -77,6 +77,11 @@ class B200DDIMScheduler(_SchedulerBase):
         c_e = math.sqrt(1.0 - a_p) - math.sqrt(a_p * (1.0 - a_t) / a_t)
         return c_x, c_e
 
+    def add_noise_coefficients(self, timestep):
+        """``add_noise(x0, noise, t) = c_x x0 + c_e noise`` ([3P] DDIMScheduler.add_noise; img2img / inpainting start latents)."""
+        a = float(self.alphas_cumprod[int(timestep)])
+        return math.sqrt(a), math.sqrt(1.0 - a)
+
     def inverse_coefficients(self, timestep, prev_timestep):
         """Inverse DDIM step x_t = c_x x + c_e eps (``_backward_ddim``, pnp_pipeline.py:73-85, :262-275)."""
         a = float(self.alphas_cumprod[int(timestep)])
@@ -129,6 +134,11 @@ class B200EulerDiscreteScheduler(_SchedulerBase):
     def _sigmas_at(self, timestep):
         i = int((self.timesteps == float(timestep)).nonzero()[0])
         return float(self.sigmas[i]), float(self.sigmas[i + 1])
+
+    def add_noise_coefficients(self, timestep):
+        """[3P] EulerDiscreteScheduler.add_noise: x0 + sigma_t noise"""
+        sigma, _ = self._sigmas_at(timestep)
+        return 1.0, sigma
 
     def input_scale(self, timestep):
         sigma, _ = self._sigmas_at(timestep)

@@ -26,13 +26,28 @@ def cfg_inputs(reqs, ip_tokens, ip_tokens_uncond):
 
 @torch.no_grad()
 def generate(unet, latents, ctx, added, num_inference_steps=50, guidance_scale=10.0, scheduler=None,
-             trace=None, teacher=None):
+             trace=None, teacher=None, init_latents=None, strength=1.0, inpaint_mask=None):
     """-> final latents (B,4,L,L).  ``trace``: list collecting (t, x_in, eps2B, x_next) per step.
-    ``teacher``: optional list of per-step input latents (teacher forcing for per-step parity)."""
+    ``teacher``: optional list of per-step input latents (teacher forcing for per-step parity).
+    ``init_latents`` + ``strength``: [3P] StableDiffusionXLImg2ImgPipeline semantics (get_timesteps + add_noise; the refiner call
+    at pipeline.py:358-361).  ``inpaint_mask`` (B,1,L,L, 1 = repaint): [3P] StableDiffusionXLInpaintPipeline with a 4-channel UNet
+    (gdino/lib.py:85-102): after every step ``latents = (1 - m) * add_noise(init, noise, t_next) + m * latents``."""
     s = scheduler or DDIMSchedulerOracle()
     s.set_timesteps(num_inference_steps)
-    x = latents * s.init_noise_sigma
-    for i, t in enumerate(s.timesteps):
+    timesteps = s.timesteps
+    noise = latents
+    if init_latents is None:
+        x = latents * s.init_noise_sigma
+    else:
+        n_run = min(int(num_inference_steps * strength), num_inference_steps)
+        timesteps = timesteps[max(num_inference_steps - n_run, 0):]
+        if strength >= 1.0 and inpaint_mask is not None:
+            x = noise * s.init_noise_sigma
+        else:
+            x = s.add_noise(init_latents, noise, timesteps[0])
+        if hasattr(s, "_step_index"):
+            s._step_index = None
+    for i, t in enumerate(timesteps):
         if teacher is not None:
             x = teacher[i]
         x_in = s.scale_model_input(torch.cat([x] * 2), t)
@@ -40,6 +55,9 @@ def generate(unet, latents, ctx, added, num_inference_steps=50, guidance_scale=1
         e_u, e_c = eps2.chunk(2)
         eps = e_u + guidance_scale * (e_c - e_u)
         x_next = s.step(eps, t, x, eta=0.0)[0]
+        if inpaint_mask is not None:
+            keep = init_latents if i + 1 >= len(timesteps) else s.add_noise(init_latents, noise, timesteps[i + 1])
+            x_next = (1 - inpaint_mask) * keep + inpaint_mask * x_next
         if trace is not None:
             trace.append(dict(t=int(t), x=x.clone(), eps2=eps2.clone(), x_next=x_next.clone()))
         x = x_next

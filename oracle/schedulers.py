@@ -111,6 +111,15 @@ class DDIMSchedulerOracle(_Base):
         return (prev,)
 
 
+def _ddim_add_noise(self, original, noise, timestep):
+    """[3P] DDIMScheduler.add_noise: sqrt(a_t) x0 + sqrt(1 - a_t) noise (img2img / inpainting start and re-noising)."""
+    a = self.alphas_cumprod[int(timestep)]
+    return a ** 0.5 * original + (1 - a) ** 0.5 * noise
+
+
+DDIMSchedulerOracle.add_noise = _ddim_add_noise
+
+
 class DDPMSchedulerOracle(_Base):
     """DDPMScheduler.step with variance_type="fixed_small" (SURVEY.md A.5)."""
 
@@ -187,6 +196,11 @@ class EulerDiscreteSchedulerOracle:
         if self._step_index is None:
             self._step_index = int((self.timesteps == float(t)).nonzero()[0])
         return self._step_index
+
+    def add_noise(self, original, noise, timestep):
+        """[3P] EulerDiscreteScheduler.add_noise: x0 + sigma_t noise"""
+        i = int((self.timesteps == float(timestep)).nonzero()[0])
+        return original + self.sigmas[i] * noise
 
     def scale_model_input(self, sample, t):
         sigma = self.sigmas[self._index(t)]
