@@ -36,6 +36,7 @@ WORKLOADS = {
     "c2": dict(L=64, B=1, prior=False, name="SDXL-class UNet 512^2 (64x64 latent) 50-step DDIM CFG, batch 1"),
     "c3": dict(L=128, B=4, prior=False, name="SDXL-class UNet 1024^2 (128x128 latent) 50-step DDIM CFG, decoupled image+text cross-attn, batch 4"),
     "c4": dict(L=128, B=8, prior=True, name="instruction-edit: prior + 1024^2 UNet sampling, batch 8 per GPU"),
+    "b1": dict(L=128, B=1, prior=False, name="single interactive request: SDXL-class UNet 1024^2 50-step DDIM CFG, batch 1"),
 }
 
 
