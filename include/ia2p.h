@@ -126,6 +126,15 @@ int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64
  * statistics pass over it.  Tiles follow the output pixel order (128 consecutive pixels; needs H*W % 128 == 0 to be usable by
  * GroupNorm); conv_up2x writes 4 segments, one per output parity. */
 
+/* Split-K workspace for the tensor-core kernels (optional).  Problems with few output rows (fewer 128 x BLOCK_N tiles than half
+ * the SMs: batch-1 512^2, single interactive requests) are otherwise bound by the latency of one tile's K loop; with a workspace
+ * every tile is computed by up to 8 CTAs over disjoint k-ranges, the partial accumulators meet in `workspace` and split 0 adds them
+ * in a fixed order (bit-reproducible) before the normal epilogue.  workspace: device memory, 256-byte aligned,
+ * ia2p_tc_workspace_bytes() bytes, its first 16 KB ZEROED once by the caller (tile arrival counters, self-resetting); it stays
+ * registered for this host thread until replaced (NULL clears) and must only be used by ONE stream at a time. */
+int64_t ia2p_tc_workspace_bytes(void);
+int ia2p_set_tc_workspace(void* workspace, int64_t bytes);
+
 /* One-shot hint for the NEXT ia2p_gemm_* / ia2p_conv* call made by this host thread: that launch also pulls `bytes` of
  * `next_weights` (the weight matrix of the tensor-core launch that will follow it) into L2, so the following kernel's first
  * wave does not start on cold DRAM misses (each layer's weights are touched once per step and never survive in L2).  The
@@ -139,7 +148,7 @@ int64_t ia2p_conv_colstats_tiles(int64_t B, int64_t Ho, int64_t Wo);
 /* ia2p_gemm_bf16 + LayerNorm folding (replaces [3P] BasicTransformerBlock.norm1/2/3 followed by to_q/k/v, attn2.to_q and
  * the GEGLU projection -- SURVEY A.3 -- without a separate normalisation pass):
  *   PRODUCER (a GEMM writing the fp32 residual stream): out_bf16 (row pitch ldo2) receives a bf16 copy of the output rows and
- *     stats_out[M][ia2p_gemm_ln_parts(M, N)][2] the per-row partial (sum, sum of squares) of every column half-tile.
+ *     stats_out[M][ia2p_gemm_ln_parts(M, N, K)][2] the per-row partial (sum, sum of squares) of every column half-tile.
  *   CONSUMER: A = those raw bf16 rows, W = bf16(W_linear * gamma) (host pre-scaled), ln_c1[n] = sum_k W[n,k], bias[n] must
  *     already contain W_linear @ beta; the epilogue applies  rstd[m] * (acc - mean[m] * ln_c1[n]) + bias[n]  (before GEGLU)
  *     with mean / rstd of row m reduced, in fixed order, from ln_stats[M][ln_parts][2]; normalised width = K1 + K2.
@@ -151,7 +160,7 @@ int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, in
                       void* out_bf16, int64_t ldo2, float* stats_out, float* colstats,
                       const float* ln_stats, int64_t ln_parts, const float* ln_c1, float ln_eps, void* stream);
 /* number of (sum, sumsq) partials per row a producer with N output columns writes */
-int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N);   /* depends on the tile width the producer picks for (M, N) */
+int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N, int64_t K);   /* depends on the tile width the producer picks for (M, N, K) */
 
 /* 3x3 conv (pad 1, stride 1|2) on NHWC bf16 as implicit GEMM, with an optional fused 1x1 shortcut conv
  * (extra K range) over up to two raw sources, bias, per-image channel bias (time embedding) and residual.

@@ -37,7 +37,9 @@ SIGNATURES = {
     "ia2p_gemm_bf16": ([_p, _l, _l, _p, _l, _l, _p, _p, _l, _l, _l, _p, _p, _l, _p, _l, _i, _i, _i, _p], _i),
     "ia2p_gemm_ln_bf16": ([_p, _l, _l, _p, _l, _l, _p, _p, _l, _l, _l, _p, _p, _l, _p, _l, _i, _i, _i,
                            _p, _l, _p, _p, _p, _l, _p, _f, _p], _i),
-    "ia2p_gemm_ln_parts": ([_l, _l], _l),
+    "ia2p_gemm_ln_parts": ([_l, _l, _l], _l),
+    "ia2p_tc_workspace_bytes": ([], _l),
+    "ia2p_set_tc_workspace": ([_p, _l], _i),
     "ia2p_conv_colstats_tiles": ([_l, _l, _l], _l),
     "ia2p_tc_prefetch_hint": ([_p, _l], _i),
     "ia2p_conv3x3_nhwc_bf16": ([_p, _l, _l, _l, _l, _i, _p, _p, _l, _p, _l, _p, _i, _l, _p, _p, _p, _i, _p, _p], _i),

@@ -41,6 +41,12 @@ struct TcParams {
   // Tail split (wave quantisation): work items [0, full_items) are whole 128 x BLOCK_N tiles; the remaining tiles -- the
   // ones that would form a last, mostly idle wave -- are cut into `split` column slices each, so that every SM gets a slice.
   int full_items, total_items, split;
+  // Split-K (few-row problems: fewer tiles than half the SMs).  Every tile is computed by `ksplit` CTAs, each over kb_per
+  // consecutive k-blocks; splits 1.. dump their fp32 accumulators to `ws` and bump flags[tile]; split 0 waits for them, adds
+  // the partials in split order (bit-reproducible), writes the sums back to TMEM and runs the normal epilogue.
+  int ksplit, kb_per;
+  float* ws;
+  unsigned* flags;
   int trace_id;                    // debug build: launch id for the in-graph timeline
   // Weight prefetch hint (ia2p_tc_prefetch_hint): the NEXT tcgen05 launch's weight matrix.  Every CTA pulls its slice into L2
   // once its first tile's loads are under way, so the next kernel's first wave does not start on cold DRAM misses.
@@ -124,6 +130,83 @@ struct TcCfg {
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
+constexpr int kEpiWarpsConst = 8;
+constexpr int kMaxKSplit = 4;
+// Split-K fix-up, run by the 8 epilogue warps before the normal epilogue (warp = TMEM lane quarter q x column half).
+// Partial storage layout per (tile, split >= 1): [BLOCK_N / 32 chunks][4][128 rows][8 floats], so that lane r of a warp moves
+// consecutive 32-byte pieces (fully coalesced both ways).  Returns true when this CTA only produced a partial.
+template <int BLOCK_N>
+__device__ __forceinline__ bool splitk_prepass(const TcParams& p, int unit, int sidx, uint32_t tmem_acc, int warp, int lane) {
+  constexpr int NCH = BLOCK_N / 32, NCH0 = (NCH + 1) / 2;
+  const int q = warp & 3, hf = (warp - 2) >> 2, row = q * 32 + lane;
+  const int c_lo = hf == 0 ? 0 : NCH0, c_hi = hf == 0 ? NCH0 : NCH;
+  const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
+  const size_t per_split = (size_t)NCH * 4 * 128 * 8;                       // floats per (tile, split)
+  float* base = p.ws + (size_t)unit * (p.ksplit - 1) * per_split;
+  if (sidx > 0) {
+    float* dst = base + (size_t)(sidx - 1) * per_split;
+    for (int c = c_lo; c < c_hi; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) stg256(dst + ((size_t)(c * 4 + i) * 128 + row) * 8, reinterpret_cast<const float*>(&v[8 * i]));
+    }
+    tc_fence_before();
+    named_bar_sync(3, 32 * kEpiWarpsConst);
+    if (warp == 2 && lane == 0) {
+      __threadfence();
+      atomicAdd(p.flags + unit, 1u);
+    }
+#ifdef IA2P_TC_TRACE
+    if (warp == 2) TRACE_PUT(10, gtime_ns());
+#endif
+    return true;
+  }
+#ifdef IA2P_TC_TRACE
+  if (warp == 2) TRACE_PUT(11, gtime_ns());
+#endif
+  if (warp == 2 && lane == 0) {
+    long long t0 = clock64();
+    while (ld_acquire_gpu(p.flags + unit) < (unsigned)(p.ksplit - 1)) {
+      if (clock64() - t0 > 20000000000LL) __trap();                          // protocol bug -> launch failure, not a hang
+    }
+    p.flags[unit] = 0u;                                                      // every partial has arrived: re-arm for the next launch
+  }
+  named_bar_sync(3, 32 * kEpiWarpsConst);
+#ifdef IA2P_TC_TRACE
+  if (warp == 2) TRACE_PUT(12, gtime_ns());
+#endif
+  for (int c = c_lo; c < c_hi; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    // all partial pieces of this chunk are requested before the first add (<= 3 splits x 4 x 32 bytes in flight per thread)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float d[kMaxKSplit - 1][8];
+#pragma unroll
+      for (int sp = 0; sp < kMaxKSplit - 1; ++sp)
+        if (sp + 1 < p.ksplit) ldg256_cg(base + (size_t)sp * per_split + ((size_t)(c * 4 + i) * 128 + row) * 8, d[sp]);
+#pragma unroll
+      for (int sp = 0; sp < kMaxKSplit - 1; ++sp)
+        if (sp + 1 < p.ksplit) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[8 * i + k] = __float_as_uint(__uint_as_float(v[8 * i + k]) + d[sp][k]);
+        }
+    }
+    tmem_st_32x32(t_row + (uint32_t)(c * 32), v);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  named_bar_sync(3, 32 * kEpiWarpsConst);                                    // other warps read these columns in the epilogue proper
+  tc_fence_after();
+#ifdef IA2P_TC_TRACE
+  if (warp == 2) TRACE_PUT(13, gtime_ns());
+#endif
+  return false;
+}
+
 constexpr int kEpiWarps = 8;                            // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 
@@ -188,7 +271,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   // tile walk: CG = 2 steps over tile PAIRS (two consecutive m-tiles); this CTA owns m_tile = 2 * pair + rank
   const int total_tiles = p.total_items;
-  const int unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
+  const bool splitk = (CG == 1) && p.ksplit > 1;                // one (tile, k-range) item per CTA
+  const int unit0 = splitk ? (int)blockIdx.x / p.ksplit : (int)blockIdx.x / CG;
+  const int unit_step = splitk ? (1 << 30) : (int)gridDim.x / CG;
+  const int sidx = splitk ? (int)blockIdx.x % p.ksplit : 0;
+  const int kb0 = sidx * p.kb_per;                              // this CTA's k-block range [kb0, kb1)
+  const int kb1 = splitk ? (kb0 + p.kb_per < p.num_kb ? kb0 + p.kb_per : p.num_kb) : p.num_kb;
   const int TB = 128 >> (p.tw_log2 + p.th_log2);
 
   if (warp == 0) {
@@ -207,10 +295,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int n0 = ti.n_tile * BLOCK_N + ti.n_off + (int)rank * (ti.w / CG);   // this CTA's slice of the B rows
       const CUtensorMap* wm = (ti.w == BLOCK_N) ? &maps.w : &maps.w2;
       const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + (ti.w / CG) * 128);
+      int kbi = 0;
       for (int e = 0; e < p.ntaps; ++e) {
         const TapEntry t = p.taps[e];
         const CUtensorMap* am = &maps.a[t.map_id];
-        for (int c = 0; c < t.nchunks; ++c) {
+        for (int c = 0; c < t.nchunks; ++c, ++kbi) {
+          if (kbi < kb0 || kbi >= kb1) continue;          // split-K: another CTA owns this k-block
           TRACE_T0(tw0);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           TRACE_ADD(tr_wait_empty, tw0);
@@ -269,7 +359,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
       const uint32_t idesc = (tile < p.full_items) ? idesc_full : idesc_half;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int nkb = kb1 - kb0;
+      for (int kb = 0; kb < nkb; ++kb) {
         TRACE_T0(tf0);
         mbar_wait(full_bar(stage), phase);
         TRACE_ADD(tr_wait_full, tf0);
@@ -285,10 +376,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
           if (CG == 2) {
             umma_commit_2sm_mc(empty_bar(stage), 3);             // frees this stage in BOTH CTAs
-            if (kb == p.num_kb - 1) umma_commit_2sm_mc(tfull_bar(buf), 3);
+            if (kb == nkb - 1) umma_commit_2sm_mc(tfull_bar(buf), 3);
           } else {
             umma_commit(empty_bar(stage));
-            if (kb == p.num_kb - 1) umma_commit(tfull_bar(buf));
+            if (kb == nkb - 1) umma_commit(tfull_bar(buf));
           }
         }
         __syncwarp();
@@ -328,6 +419,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
+      if (CG == 1 && splitk) {                               // sum the k-range partials first (or hand ours over and stop)
+        mbar_wait(tfull_bar(buf), use & 1u);
+        tc_fence_after();
+        if (splitk_prepass<BLOCK_N>(p, tile, sidx, tmem_base + (uint32_t)(buf * BLOCK_N), warp, lane)) continue;
+      }
       const int m_tile = ti.m_unit * CG + (int)rank;
       const int xt = m_tile % p.tiles_x;
       const int r = m_tile / p.tiles_x;
@@ -545,6 +641,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
+      if (CG == 1 && splitk) {                               // sum the k-range partials first (or hand ours over and stop)
+        mbar_wait(tfull_bar(buf), use & 1u);
+        tc_fence_after();
+        if (splitk_prepass<BLOCK_N>(p, tile, sidx, tmem_base + (uint32_t)(buf * BLOCK_N), warp, lane)) continue;
+      }
       const int n_tile = ti.n_tile;
       const int m_tile = ti.m_unit * CG + (int)rank;
       const int xt = m_tile % p.tiles_x;
@@ -777,6 +878,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   }
 #ifdef IA2P_TC_TRACE
   if (threadIdx.x == 0 && g_tc_timeline != nullptr) atomicMax(g_tc_timeline + 2 * (size_t)p.trace_id + 1, gtime_ns());
+  if (warp == 0) TRACE_PUT(14, gtime_ns());                                 // after the final barrier: the CTA's true end
 #endif
 }
 
@@ -829,20 +931,51 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 // few output rows (batch-1 512^2: M = 512 -> 4 row tiles) fall through to the narrowest one, so that e.g. the FF-out GEMM
 // (N 1280, K 5120) streams its weights through 80 CTAs instead of 20.
 constexpr int kMinTilesForWideBlock = 120;
-static int pick_block_n(int64_t N, bool geglu, int64_t m_tiles) {
+constexpr int kSplitKMinKb = 40;                         // split-K only from K >= 2560 on
+static bool splitk_enabled();
+static int pick_block_n(int64_t N, bool geglu, int64_t m_tiles, int num_kb = 0) {
   if (const char* e = getenv("IA2P_GEMM_BN")) {          // experiments only
     const int v = atoi(e);
     if ((v == 64 || v == 128 || v == 160 || v == 256) && N % v == 0 && (!geglu || v % 64 == 0)) return v;
   }
   const int cand[4] = {256, 160, 128, 64};
-  int last = 0;
+  int last = 0, first = 0;
   for (int i = 0; i < 4; ++i) {
     const int c = cand[i];
     if (N % c != 0 || (geglu && c % 64 != 0)) continue;
+    if (first == 0) first = c;
     last = c;
     if (m_tiles * (N / c) >= kMinTilesForWideBlock) return c;
   }
+  // too few tiles at every width: with a split-K workspace keep the WIDEST tile (best operand reuse) and fill the SMs with
+  // k-range splits instead of narrow tiles
+  if (first != 0 && num_kb >= kSplitKMinKb && splitk_enabled() && m_tiles * (N / first) * 2 <= sm_count()) return first;
   return last != 0 ? last : 128;                         // 128 with a ragged last tile when nothing divides N
+}
+
+// Split-K workspace (ia2p_set_tc_workspace): [16 KB of tile flags, zero-initialised by the caller][partial accumulators]
+static thread_local void* g_ws_ptr = nullptr;
+static thread_local long long g_ws_bytes = 0;
+constexpr long long kWsFlagBytes = 16384;
+static bool splitk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA2P_GEMM_SPLITK");          // experiments only: 0 disables
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0 && g_ws_ptr != nullptr;
+}
+// k-range splits for a problem of `units` tiles (single-CTA kernel) and num_kb k-blocks; 1 = no split
+static int pick_ksplit(long long units, int num_kb, int bn) {
+  // A split costs a dump + a fix-up pass (~2 us + ~2 us per extra split) and saves (1 - 1/ks) of the K loop (~0.35 us per
+  // k-block): worth it from ~16 k-blocks per split on (measured: 7 splits of a 20-k-block out-projection ran 2x SLOWER).
+  if (!splitk_enabled() || units * 2 > sm_count() || num_kb < kSplitKMinKb || units > kWsFlagBytes / 4) return 1;
+  int ks = (int)(sm_count() / units);
+  if (ks > num_kb / 16) ks = num_kb / 16;
+  if (ks > kMaxKSplit) ks = kMaxKSplit;
+  const long long per = (long long)bn * 128 * 4;         // bytes of one partial tile
+  while (ks > 1 && units * (ks - 1) * per > g_ws_bytes - kWsFlagBytes) --ks;
+  return ks < 2 ? 1 : ks;
 }
 
 static thread_local const void* g_pf_ptr = nullptr;
@@ -876,15 +1009,30 @@ static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
   p.full_items = units;
   p.total_items = units;
   p.split = 1;
+  p.ksplit = 1;
+  p.kb_per = p.num_kb;
+  p.ws = nullptr;
+  p.flags = nullptr;
+  int grid_override = 0;
+  if (CG == 1) {
+    const int ks = pick_ksplit(units, p.num_kb, BN);
+    if (ks > 1) {
+      p.kb_per = (p.num_kb + ks - 1) / ks;
+      p.ksplit = (p.num_kb + p.kb_per - 1) / p.kb_per;
+      p.flags = static_cast<unsigned*>(g_ws_ptr);
+      p.ws = reinterpret_cast<float*>(static_cast<char*>(g_ws_ptr) + kWsFlagBytes);
+      grid_override = units * p.ksplit;
+    }
+  }
   const int rem = units % max_units;
-  const bool can_split = tail_split_enabled() && (BN % 64 == 0) && (!p.geglu || BN % 128 == 0) && (p.N % BN == 0);
+  const bool can_split = p.ksplit == 1 && tail_split_enabled() && (BN % 64 == 0) && (!p.geglu || BN % 128 == 0) && (p.N % BN == 0);
   if (can_split && units > max_units && rem != 0 && 2 * rem <= max_units) {
     p.split = 2;
     p.full_items = units - rem;
     p.total_items = p.full_items + 2 * rem;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
+  cfg.gridDim = dim3((unsigned)(grid_override ? grid_override : grid));
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
@@ -921,6 +1069,7 @@ static bool use_pair(int m_tiles, int num_kb, int64_t N, int bn) {
     v = (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '2') ? 2 : 0;
   }
   if (m_tiles < 2 || bn == 64) return false;                      // BLOCK_N 64 exists for small problems only: single CTA
+  if (pick_ksplit((int64_t)m_tiles * ((N + bn - 1) / bn), num_kb, bn) > 1) return false;   // split-K runs on the single-CTA kernel
   if (v == 0 && (int64_t)m_tiles * ((N + bn - 1) / bn) < 2 * sm_count()) return false;   // too few tiles to pair up
   return v == 2 || (v == 0 && num_kb > 12);
 }
@@ -1021,6 +1170,19 @@ extern "C" int ia2p_debug_set_trace(void* dev_buffer) {       // debug build onl
 }
 #endif
 
+extern "C" int64_t ia2p_tc_workspace_bytes(void) { return 64ll << 20; }
+
+extern "C" int ia2p_set_tc_workspace(void* workspace, int64_t bytes) {
+  if (workspace == nullptr || bytes <= kWsFlagBytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    g_ws_ptr = nullptr;
+    g_ws_bytes = 0;
+    return workspace == nullptr ? 0 : IA2P_E_ARG;
+  }
+  g_ws_ptr = workspace;
+  g_ws_bytes = bytes;
+  return 0;
+}
+
 extern "C" int ia2p_tc_prefetch_hint(const void* next_weights, int64_t bytes) {
   g_pf_ptr = (bytes >= 16 && (reinterpret_cast<uintptr_t>(next_weights) & 15) == 0) ? next_weights : nullptr;
   g_pf_bytes = g_pf_ptr ? (bytes & ~15LL) : 0;
@@ -1035,8 +1197,8 @@ extern "C" int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void
                            out_dtype, epilogue, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0.f, stream);
 }
 
-extern "C" int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N) {
-  const int bn = pick_block_n(N, false, (M + 127) / 128);
+extern "C" int64_t ia2p_gemm_ln_parts(int64_t M, int64_t N, int64_t K) {
+  const int bn = pick_block_n(N, false, (M + 127) / 128, (int)(K / 64));
   return 4 * ((N + bn - 1) / bn);
 }
 
@@ -1071,7 +1233,7 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
   IA2P_REQUIRE(rowbias == nullptr || rows_per_batch > 0, IA2P_E_ARG, "gemm: rowbias needs rows_per_batch");
   IA2P_REQUIRE(M < (1ll << 31) && N < (1ll << 31), IA2P_E_SHAPE, "gemm: M/N too large");
 
-  const int bn = pick_block_n(N, geglu, (M + 127) / 128);
+  const int bn = pick_block_n(N, geglu, (M + 127) / 128, (int)((K1 + K2) / 64));
   TcMaps maps;
   TcParams p{};
   {
@@ -1134,7 +1296,7 @@ static int conv3x3_impl(const void* x, int64_t B, int64_t H, int64_t W, int64_t 
   int TH = 1; while (TW * TH < 128 && Ho % (TH * 2) == 0) TH *= 2;
   const int TB = 128 / (TW * TH);
   const int64_t Ktot = 9 * Cin + sc_ca + sc_cb;
-  const int bn = pick_block_n(Cout, false, (Wo / TW) * (Ho / TH) * ((B + TB - 1) / TB));
+  const int bn = pick_block_n(Cout, false, (Wo / TW) * (Ho / TH) * ((B + TB - 1) / TB), (int)(Ktot / 64));
 
   TcMaps maps;
   TcParams p{};
@@ -1225,7 +1387,7 @@ extern "C" int ia2p_conv_up2x_nhwc_bf16(const void* x, int64_t B, int64_t H, int
   int TH = 1; while (TW * TH < 128 && H % (TH * 2) == 0) TH *= 2;
   const int TB = 128 / (TW * TH);
   const int64_t Ktot = 4 * Cin;
-  const int bn = pick_block_n(Cout, false, (W / TW) * (H / TH) * ((B + TB - 1) / TB));
+  const int bn = pick_block_n(Cout, false, (W / TW) * (H / TH) * ((B + TB - 1) / TB), (int)(Ktot / 64));
   const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(w4);

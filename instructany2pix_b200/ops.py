@@ -292,6 +292,29 @@ def layernorm(x, gamma, beta, eps, out_dtype=None):
 
 
 # ------------------------------------------------------------------------------------------------ tensor-core GEMM / conv
+# split-K workspace of the tensor-core kernels: one per device (the hot path runs on ONE stream per process), registered with the
+# library before every tc launch made through this module (a thread-local pointer on the library side; re-registering is ~ns)
+# Measured on B200 (tools/small_m.py, small_m_timeline.py; M 512, N 1280, K 5120): the k-loop shrinks 25 -> 9 us with 4 splits, but
+# the hand-over (+6 us), the fix-up reads (+8 us) and the now fully exposed 128 x 256 epilogue (+13 us) make the launch SLOWER
+# (37 vs 29 us; c2 step 13.9 vs 13.4 ms) than one narrow tile per CTA.  Kept opt-in (IA2P_GEMM_SPLITK=1) for the next round.
+USE_SPLITK = os.environ.get("IA2P_GEMM_SPLITK", "0") == "1"
+_TC_WS = {}
+
+
+def _ensure_tc_workspace(device):
+    if not USE_SPLITK:
+        return
+    lib = _lib.load()
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    ws = _TC_WS.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return                                     # never allocate inside a graph capture: this call runs without split-K
+        ws = torch.zeros(int(lib.ia2p_tc_workspace_bytes()), device=device, dtype=torch.uint8)
+        _TC_WS[key] = ws
+    lib.ia2p_set_tc_workspace(ws.data_ptr(), ws.numel())
+
+
 def _colstats_buffer(tiles, n, device):
     """[row tiles][n][2] fp32 for the per-tile column sums a producer epilogue emits (consumed by groupnorm); None if tiles == 0"""
     return torch.empty(tiles, n, 2, device=device, dtype=torch.float32) if tiles > 0 else None
@@ -308,6 +331,7 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
     lib = _lib.load()
     _need(a, torch.bfloat16, "a", 2)
     _need(w, torch.bfloat16, "w", 2)
+    _ensure_tc_workspace(a.device)
     assert w.is_contiguous()
     M, K1 = a.shape
     N = w.shape[0]
@@ -335,7 +359,7 @@ def gemm(a, w, bias=None, a2=None, rowbias=None, rows_per_batch=0, residual=None
     if want_ln:
         assert not geglu
         out2 = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
-        stats = torch.empty(M, int(lib.ia2p_gemm_ln_parts(M, N)), 2, device=a.device, dtype=torch.float32)
+        stats = torch.empty(M, int(lib.ia2p_gemm_ln_parts(M, N, K1 + K2)), 2, device=a.device, dtype=torch.float32)
     cs = _colstats_buffer((M + 127) // 128, N, a.device) if (want_colstats and USE_COLSTATS and out.dtype == torch.float32 and not geglu) else None
     ln_stats = ln_c1 = None
     ln_parts, ln_eps = 0, 0.0
@@ -371,6 +395,7 @@ def conv3x3(x, w, cout, stride=1, sc_a=None, sc_b=None, bias=None, rowbias=None,
     lib = _lib.load()
     _need(x, torch.bfloat16, "x", 4)
     _need(w, torch.bfloat16, "w", 2)
+    _ensure_tc_workspace(x.device)
     x = x.contiguous()
     assert w.is_contiguous()
     B, H, W, Cin = x.shape
@@ -415,6 +440,7 @@ def conv_up2x(x, w4, cout, bias=None, want_colstats=False):
     lib = _lib.load()
     _need(x, torch.bfloat16, "x", 4)
     _need(w4, torch.bfloat16, "w4", 3)
+    _ensure_tc_workspace(x.device)
     x = x.contiguous()
     B, H, W, Cin = x.shape
     assert w4.is_contiguous() and w4.shape == (4, cout, 4 * Cin)
@@ -439,6 +465,7 @@ def conv3x3_down_padend(x, w, cout, bias=None, out_dtype=torch.bfloat16):
     lib = _lib.load()
     _need(x, torch.bfloat16, "x", 4)
     _need(w, torch.bfloat16, "w", 2)
+    _ensure_tc_workspace(x.device)
     x = x.contiguous()
     B, H, W, Cin = x.shape
     assert w.is_contiguous() and w.shape == (cout, 9 * Cin) and H % 2 == 0 and W % 2 == 0

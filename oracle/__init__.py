@@ -29,9 +29,14 @@ input/output fixtures under ``tests/golden/``.  The restatements in this
 package are pinned against those fixtures (tests/test_oracle_golden.py).
 
 Parity status: the reference ships no tests/golden vectors for this path
-(SURVEY.md section 4), so the *third-party* parts (UNet, schedulers) are
-"parity unpinned" -- pinned only structurally (exact parameter counts, DDIM
-timestep tables) and by algebraic identities; the in-tree parts (processors,
-projector, inversion step, prior wrapper) are pinned against outputs of the
-reference code itself.
+(SURVEY.md section 4).  Pinned against outputs of reference code RUN in the
+build container: the in-tree parts (processors, projector, inversion step,
+polar blend, prior wrapper) and -- through the in-tree LDM modules the
+diffusers blocks are ports of (llm/model/vae/modules; oracle/ldm_map.py) --
+ResnetBlock2D, GEGLU FF, BasicTransformerBlock, the Transformer2D wrapper, the
+VAE encoder/decoder trunks, the sinusoid, the alpha-bar table, the DDIM
+timestep tables, and DDIMScheduler.step (as the inverse of the reference's
+``_backward_ddim``).  Still "parity unpinned" (restated from the published
+diffusers 0.26.3 semantics, pinned only structurally): the assembly of those
+blocks into the SDXL UNet, the Euler scheduler, the 1x1 (post_)quant convs.
 """

@@ -128,6 +128,94 @@ def gen_prior():
     np.savez_compressed(os.path.join(OUT, "prior.npz"), **out)
 
 
+# ---------------------------------------------------------------------------------------------- in-tree LDM blocks
+# The diffusers blocks of the hot path are absent from /root/reference, but the LDM modules they are ports of are in-tree
+# (llm/model/vae/modules).  Each case below builds the ORACLE module, draws its name-seeded weights, renames them
+# (oracle/ldm_map.py) into the reference module and records what the reference computes.
+LDM_VAE_CFG = dict(latent_channels=4, out_channels=3, block_out_channels=(64, 64, 128, 128), layers_per_block=1,
+                   norm_num_groups=32, scaling_factor=0.13025)
+LDM_RES_CASES = [("res_64_128", 64, 128, 96), ("res_64_64", 64, 64, 96)]       # name, cin, cout, temb width
+LDM_TBLOCK = dict(dim=128, heads=2, ctx_dim=96, depth=2, tokens_hw=(6, 5), ctx_tokens=11, batch=2)
+
+
+def ldm_oracle_modules():
+    """the oracle modules of every LDM case with their name-seeded weights loaded: {case: module}"""
+    from . import unet as U
+    from .vae import OracleVAEDecoder, OracleVAEEncoder
+    mods = {}
+    for name, cin, cout, tw in LDM_RES_CASES:
+        mods[name] = U.ResnetBlock2D(cin, cout, tw, 32, 1e-6)        # LDM Normalize: eps 1e-6 (SURVEY A.7)
+    mods["ff"] = U.FeedForward(LDM_TBLOCK["dim"])
+    mods["tblock"] = U.BasicTransformerBlock(LDM_TBLOCK["dim"], LDM_TBLOCK["heads"], LDM_TBLOCK["ctx_dim"])
+    mods["t2d"] = U.Transformer2DModel(LDM_TBLOCK["dim"], LDM_TBLOCK["heads"], LDM_TBLOCK["depth"], LDM_TBLOCK["ctx_dim"], 32)
+    mods["vae_dec"] = OracleVAEDecoder(LDM_VAE_CFG)
+    mods["vae_enc"] = OracleVAEEncoder(LDM_VAE_CFG)
+    for i, (k, m) in enumerate(sorted(mods.items())):
+        m.load_state_dict(synth_state_dict(m, 40 + i))
+        m.eval()
+    return mods
+
+
+def ldm_inputs():
+    T = LDM_TBLOCK
+    h, w = T["tokens_hw"]
+    return dict(
+        res_x=synth_input("ldm/res/x", (2, 64, 12, 10)), res_temb=synth_input("ldm/res/temb", (2, 96)),
+        tok=synth_input("ldm/tok", (T["batch"], h * w, T["dim"])), ctx=synth_input("ldm/ctx", (T["batch"], T["ctx_tokens"], T["ctx_dim"])),
+        map=synth_input("ldm/map", (T["batch"], T["dim"], h, w)),
+        z=synth_input("ldm/z", (2, 4, 6, 4)), img=synth_input("ldm/img", (2, 3, 32, 48)),
+        t=torch.tensor([0.0, 1.0, 21.0, 981.0, 999.0, 500.5]),
+    )
+
+
+def gen_ldm():
+    from . import ldm_map as M
+    B, A, Ut = ref_shims.load_ldm_modules()
+    mods, x = ldm_oracle_modules(), ldm_inputs()
+    out = {}
+
+    def load(ref, sd):
+        missing, unexpected = ref.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+        return ref.eval()
+
+    for name, cin, cout, tw in LDM_RES_CASES:
+        ref = load(B.ResnetBlock(in_channels=cin, out_channels=cout, dropout=0.0, temb_channels=tw), M.resnet_to_ldm(mods[name].state_dict()))
+        out[name] = ref(x["res_x"], x["res_temb"]).numpy()
+    T = LDM_TBLOCK
+    dh = T["dim"] // T["heads"]
+    out["ff"] = load(A.FeedForward(T["dim"], glu=True), mods["ff"].state_dict())(x["tok"]).numpy()
+    ref = load(A.BasicTransformerBlock(T["dim"], T["heads"], dh, context_dim=T["ctx_dim"], checkpoint=False), mods["tblock"].state_dict())
+    out["tblock"] = ref(x["tok"], context=x["ctx"]).numpy()
+    ref = load(A.SpatialTransformer(T["dim"], T["heads"], dh, depth=T["depth"], context_dim=T["ctx_dim"]), M.transformer2d_to_ldm(mods["t2d"].state_dict()))
+    for blk in ref.transformer_blocks:
+        blk.checkpoint = False
+    out["t2d"] = ref(x["map"], context=x["ctx"]).numpy()
+    ch = LDM_VAE_CFG["block_out_channels"]
+    kw = dict(ch=ch[0], out_ch=3, ch_mult=tuple(c // ch[0] for c in ch), num_res_blocks=LDM_VAE_CFG["layers_per_block"],
+              attn_resolutions=[], in_channels=3, resolution=256, z_channels=4)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):       # the constructors print
+        dec, enc = B.Decoder(**kw), B.Encoder(**kw, double_z=True)
+    sd = {k: v for k, v in mods["vae_dec"].state_dict().items() if not k.startswith("post_quant_conv")}
+    out["vae_dec"] = load(dec, M.vae_decoder_to_ldm(sd, len(ch)))(x["z"]).numpy()
+    sd = {k: v for k, v in mods["vae_enc"].state_dict().items() if not k.startswith("quant_conv")}
+    out["vae_enc"] = load(enc, M.vae_encoder_to_ldm(sd, len(ch)))(x["img"]).numpy()
+    # scalar tables: sinusoid (util.py:271-292 = diffusers flip_sin_to_cos=True, shift 0), SDXL "scaled_linear" betas
+    # (util.py:141-145 "linear", fp64), DDIM "uniform" timesteps + 1 (util.py:166-180 = leading spacing, steps_offset 1)
+    out["sinusoid_320"] = Ut.timestep_embedding(x["t"], 320).numpy()
+    out["sinusoid_256"] = Ut.timestep_embedding(x["t"], 256).numpy()
+    betas = Ut.make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.012)
+    out["alphas_cumprod"] = np.cumprod(1.0 - betas, axis=0)
+    out["ddim_timesteps_50"] = Ut.make_ddim_timesteps("uniform", 50, 1000, verbose=False)
+    out["ddim_timesteps_25"] = Ut.make_ddim_timesteps("uniform", 25, 1000, verbose=False)
+    _, a, a_prev = Ut.make_ddim_sampling_parameters(out["alphas_cumprod"], out["ddim_timesteps_50"], 0.0, verbose=False)
+    out["ddim_alphas_50"], out["ddim_alphas_prev_50"] = a, a_prev
+    np.savez_compressed(os.path.join(OUT, "ldm_blocks.npz"), **out)
+    print("ldm:", {k: tuple(v.shape) for k, v in out.items()})
+
+
 def main():
     assert ref_shims.available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -136,6 +224,7 @@ def main():
     gen_image_proj()
     gen_scalar_fns()
     gen_prior()
+    gen_ldm()
     print("wrote", sorted(os.listdir(OUT)))
 
 

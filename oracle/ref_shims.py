@@ -115,3 +115,23 @@ def load_prior(n_layer=24):
         GPT2Config.from_pretrained = orig
     prior.device = torch.device("cpu")
     return prior.eval(), mod, _FakeClip
+
+
+def load_ldm_modules():
+    """-> (blocks, attention, util): the reference's in-tree LDM building blocks (llm/model/vae/modules/*.py, torch + einops
+    only), imported unmodified under a private package name so that ``instructany2pix/llm/__init__.py`` (which needs the LLM
+    stack) never runs.  The diffusers UNet / AutoencoderKL blocks the hot path uses are ports of these (SURVEY A.7 lists the
+    differences), which makes them the only reference-run pin available for the restated ResnetBlock2D,
+    BasicTransformerBlock, GEGLU FF, Transformer2D wrapper, VAE Encoder/Decoder, sinusoid and beta schedule."""
+    name = "_ia2p_ref_ldm"
+    if name not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(REF_ROOT, "instructany2pix/llm/model/vae/modules")]
+        sys.modules[name] = pkg
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        blocks = importlib.import_module(name + ".blocks")
+        attention = importlib.import_module(name + ".attention")
+        util = importlib.import_module(name + ".util")
+    return blocks, attention, util

@@ -90,7 +90,9 @@ class _Base:
 
 
 class DDIMSchedulerOracle(_Base):
-    """DDIMScheduler.step, eta / variance-noise supported."""
+    """DDIMScheduler.step, eta / variance-noise supported.  Pinned (eta = 0) as the exact inverse of the
+    reference's own ``_backward_ddim`` (ddim/pnp_pipeline.py:73-85) on its golden outputs:
+    tests/test_oracle_golden.py::test_ddim_step_inverts_reference_backward_ddim."""
 
     def step(self, model_output, timestep, sample, eta=0.0, generator=None,
              variance_noise=None, return_dict=False):

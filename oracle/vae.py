@@ -2,7 +2,11 @@
 latents into images for the north-star PSNR gate ("decoded image PSNR >= 35 dB, same decoder on both latents").
 
 Third-party algorithm (requirements.txt:3), reference call site ddim/sdxl_pipeline.py:859-871 (``vae.decode(latents /
-scaling_factor)``, fp32 upcast).  Parity unpinned (no golden vectors exist); structure follows the published SDXL VAE config:
+scaling_factor)``, fp32 upcast).  The diffusers module itself is absent, but it is a key-renamed port of the LDM
+``Encoder`` / ``Decoder`` the reference carries in-tree (llm/model/vae/modules/blocks.py:369-570): both trunks are PINNED
+against that code run in the build container (oracle/gen_golden.py::gen_ldm -> tests/golden/ldm_blocks.npz,
+tests/test_oracle_golden.py::test_vae_trunks_match_reference_ldm); only the two 1x1 (post_)quant convs and the SDXL channel
+widths are taken from the published config.  Structure follows the published SDXL VAE config:
 block_out_channels (128,256,512,512), layers_per_block 2 (decoder uses 3 resnets per up block), one single-head mid attention,
 GroupNorm(32, eps 1e-6), SiLU, scaling_factor 0.13025.  ``TINY_VAE`` shrinks the widths for fast tests.
 """
@@ -84,7 +88,13 @@ class OracleVAEDecoder(nn.Module):
     @torch.no_grad()
     def decode(self, latents):
         """latents (B,4,L,L) as produced by the sampler -> images (B,3,8L,8L) in [-1, 1] nominal range."""
-        z = self.post_quant_conv(latents.float() / self.cfg["scaling_factor"])
+        return self.trunk(self.post_quant_conv(latents.float() / self.cfg["scaling_factor"]))
+
+    @torch.no_grad()
+    def trunk(self, z):
+        """``Decoder`` proper (conv_in .. conv_out).  Pinned against the reference's in-tree LDM ``Decoder``
+        (llm/model/vae/modules/blocks.py:463-570, the module diffusers' AutoencoderKL decoder is a port of) by
+        tests/golden/ldm_blocks.npz."""
         x = self.conv_in(z)
         x = self.mid_res1(self.mid_attn(self.mid_res0(x)))
         for u in self.up_blocks:
@@ -112,7 +122,8 @@ class _Down(nn.Module):
 class OracleVAEEncoder(nn.Module):
     """Restated diffusers==0.26.3 ``AutoencoderKL`` ENCODER + ``quant_conv`` + ``DiagonalGaussianDistribution`` (SDXL VAE
     config): the path ``prepare_latents`` of the inversion pipeline takes (ddim/pnp_pipeline.py:195-204:
-    ``vae.encode(image).latent_dist.sample(generator) * vae.config.scaling_factor``).  Parity unpinned (third-party module)."""
+    ``vae.encode(image).latent_dist.sample(generator) * vae.config.scaling_factor``).  The trunk is pinned against the in-tree LDM
+    ``Encoder`` (see the module header); ``quant_conv`` + the gaussian sample are restated only."""
 
     def __init__(self, cfg=None, in_channels=3):
         super().__init__()
@@ -132,11 +143,16 @@ class OracleVAEEncoder(nn.Module):
 
     @torch.no_grad()
     def moments(self, images):
+        return self.quant_conv(self.trunk(images))
+
+    @torch.no_grad()
+    def trunk(self, images):
+        """``Encoder`` proper (conv_in .. conv_out); pinned against the in-tree LDM ``Encoder`` (blocks.py:369-460)."""
         x = self.conv_in(images.float())
         for d in self.down_blocks:
             x = d(x)
         x = self.mid_res1(self.mid_attn(self.mid_res0(x)))
-        return self.quant_conv(self.conv_out(F.silu(self.conv_norm_out(x))))
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
 
     @torch.no_grad()
     def encode(self, images, noise=None):

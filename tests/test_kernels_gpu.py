@@ -92,6 +92,45 @@ def test_gemm_every_tile_width(bn, M, monkeypatch):
     assert rel(out, F.layer_norm(t, (N,), ln.weight, ln.bias, 1e-5) @ w3.float().t()) < 8e-3
 
 
+@pytest.mark.parametrize("kind", ["plain", "fp32_ln", "res_ring", "geglu", "conv", "conv_res"])
+def test_split_k_for_few_row_problems(kind, monkeypatch):
+    """(opt-in path, off by default: see ops.USE_SPLITK) fewer tiles than half the SMs -> every tile is computed by several CTAs over disjoint k-ranges; partials are summed in a
+    fixed order before the normal epilogue: same results as the one-CTA-per-tile path, bit-reproducible run to run."""
+    from instructany2pix_b200.packing import interleave_geglu, pack_conv3x3
+    monkeypatch.setattr(ops, "USE_SPLITK", True)
+    if kind == "plain":
+        a, w = rnd(384, 2560), rnd(1280, 2560, scale=2560 ** -0.5)
+        f = lambda: ops.gemm(a, w)
+        ref, tol = a.float() @ w.float().t(), TOL
+    elif kind == "fp32_ln":
+        a, w = rnd(512, 5120), rnd(1280, 5120, scale=5120 ** -0.5)
+        bias, res = rnd(1280, dtype=torch.float32), rnd(512, 1280, dtype=torch.float32)
+        f = lambda: ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, want_ln=True, want_colstats=True)[0]
+        ref, tol = a.float() @ w.float().t() + bias + res, 3e-6
+    elif kind == "res_ring":
+        a, w = rnd(256, 1280), rnd(640, 1280, scale=1280 ** -0.5)
+        res = rnd(256, 640, dtype=torch.float32)
+        f = lambda: ops.gemm(a, w, residual=res, out_dtype=torch.float32)
+        ref, tol = a.float() @ w.float().t() + res, 3e-6
+    elif kind == "geglu":
+        a, w, b = rnd(256, 1024), rnd(2560, 1024, scale=1024 ** -0.5), rnd(2560, dtype=torch.float32, scale=0.1)
+        wi, bi = interleave_geglu(w, b)
+        f = lambda: ops.gemm(a, wi, bias=bi, geglu=True)
+        h = a.float() @ w.float().t() + b
+        ref, tol = h[:, :1280] * F.gelu(h[:, 1280:]), TOL
+    else:
+        x, w = rnd(2, 16, 16, 640), rnd(1280, 640, 3, 3, scale=(9 * 640) ** -0.5)
+        res = rnd(2, 16, 16, 1280, dtype=torch.float32) if kind == "conv_res" else None
+        f = lambda: ops.conv3x3(x, pack_conv3x3(w), 1280, residual=res, out_dtype=torch.float32, want_colstats=True)
+        ref, tol = _conv_ref(x, w) + (0 if res is None else res), 3e-6
+    out = f()
+    assert rel(out, ref) < tol
+    assert torch.equal(out, f())
+    if kind == "fp32_ln":
+        t, tb, st = ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, want_ln=True)
+        assert torch.equal(tb, t.to(torch.bfloat16)) and rel(st.sum(1)[:, 0], t.sum(1)) < 1e-5
+
+
 def test_gemm_epilogues():
     M, N, K = 768, 640, 320
     a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
