@@ -157,7 +157,7 @@ def host_inputs(B, L, seed):
     g = torch.Generator()
     g.manual_seed(seed)
     pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t
-    ctx = torch.randn(2 * B, 81, 2048, generator=g)              # [neg ; pos] x (77 text + 4 IP tokens)
+    ctx = torch.randn(2 * B, 77, 2048, generator=g)              # [neg ; pos] text tokens; the 4 IP tokens are projected per request
     pooled = torch.randn(2 * B, 1280, generator=g)
     H = float(L * 8)
     tid = torch.tensor([[H, H, 0.0, 0.0, H, H]]).repeat(2 * B, 1)
@@ -167,20 +167,23 @@ def host_inputs(B, L, seed):
     return dict(ctx=pin(ctx), pooled=pin(pooled), tid=pin(tid), lat=pin(lat), llm=pin(e))
 
 
-def run_trajectory(sampler, prior, dev_in, steps):
-    if prior is not None:
-        prior.generate_diffusion(3, 0, dev_in["llm"], device=dev_in["llm"].device, dtype=torch.float32, num_inference_steps=25,
-                                 guidance_scale=10, score=6.5)
-    return sampler.generate(dev_in["lat"], dev_in["ctx"], dict(text_embeds=dev_in["pooled"], time_ids=dev_in["tid"]),
-                            num_inference_steps=steps, guidance_scale=10.0)
+def run_trajectory(hot, dev_in, steps):
+    """one request batch: (prior ->) LLM embedding -> ImageProj -> 4 IP tokens appended to the text tokens -> CFG sampling"""
+    y = None
+    if hot.prior is not None:
+        y = hot.prior.generate_diffusion(3, 0, dev_in["llm"], device=dev_in["llm"].device, dtype=torch.float32,
+                                         num_inference_steps=25, guidance_scale=10, score=6.5)[0]
+    ctx = hot.ip_context(dev_in["ctx"], dev_in["llm"], prior_embed=y)
+    return hot.sampler.generate(dev_in["lat"], ctx, dict(text_embeds=dev_in["pooled"], time_ids=dev_in["tid"]),
+                                num_inference_steps=steps, guidance_scale=10.0)
 
 
 # ------------------------------------------------------------------------------------------------ roofline of the dominant kernel
-def profile_dominant_kernel(unet, sampler, dev_in, B):
+def profile_dominant_kernel(unet, sampler, dev_in, B, ctx81):
     """CUDA events around every C-ABI launch of ONE eager UNet forward (CFG batch 2B) on the launching stream."""
     from instructany2pix_b200 import ops
     added = dict(text_embeds=dev_in["pooled"], time_ids=dev_in["tid"])
-    kv = unet.context_kv(dev_in["ctx"])
+    kv = unet.context_kv(ctx81)
     rb = unet.time_rowbias_table(torch.tensor([981.0]), added, 2 * B)[0].contiguous()
     x = dev_in["lat"].float()
     for _ in range(2):
@@ -210,9 +213,15 @@ def profile_dominant_kernel(unet, sampler, dev_in, B):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_unet_step_seconds(L, threads):
-    """One CFG UNet step (2 sample-forwards, batch 1) of the fp32 oracle restatement on the host cores."""
+_CPU_UNET = None
+
+
+def _cpu_unet(threads):
+    """the fp32 oracle restatement at SDXL-base width with decoupled cross-attention processors, built once per process"""
+    global _CPU_UNET
     torch.set_num_threads(threads)
+    if _CPU_UNET is not None:
+        return _CPU_UNET
     from oracle.attention import IPAttnProcessor2_0
     from oracle.unet import SDXL_BASE, OracleUNet
     with torch.device("meta"):
@@ -234,6 +243,15 @@ def cpu_unet_step_seconds(L, threads):
                 p.fill_(1.0)
             else:
                 p.zero_()
+    _CPU_UNET = m
+    return m
+
+
+def cpu_unet_step_seconds(L, threads):
+    """One CFG UNet step (2 sample-forwards, batch 1) + the CFG/DDIM arithmetic of the fp32 oracle restatement on the host
+    cores (model construction excluded)."""
+    m = _cpu_unet(threads)
+    with torch.no_grad():
         x = torch.randn(2, 4, L, L)
         ctx = torch.randn(2, 81, 2048)
         added = dict(text_embeds=torch.randn(2, 1280), time_ids=torch.tensor([[L * 8.0, L * 8.0, 0, 0, L * 8.0, L * 8.0]] * 2))
@@ -298,11 +316,14 @@ def main():
     torch.set_grad_enabled(False)
 
     from instructany2pix_b200 import ops
-    from instructany2pix_b200.sampler import B200Sampler
     L, B, NS = wl["L"], wl["B"], args.num_inference_steps
     unet, prior = build_models(dev, wl["prior"])
     vae = build_vae(dev)
-    sampler = B200Sampler(unet, use_cuda_graph=not args.no_graph)
+    from instructany2pix_b200.hotpath import B200HotPath
+    from instructany2pix_b200.image_proj import B200ImageProj
+    proj = B200ImageProj(device=dev)                             # Linear(1024 -> 4 x 2048) + LayerNorm(2048), PyTorch-default init
+    hot = B200HotPath(unet, vae, prior=prior, use_cuda_graph=not args.no_graph, image_proj=proj)
+    sampler = hot.sampler
     host = host_inputs(B, L, seed=1000 + rank)                   # every rank samples different prompts/seeds
     dev_in = {k: v.to(dev) for k, v in host.items()}
 
@@ -313,7 +334,7 @@ def main():
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 1)):
-        lat_w = run_trajectory(sampler, prior, dev_in, NS)
+        lat_w = run_trajectory(hot, dev_in, NS)
     vae.decode(lat_w)                                            # warm-up of the decode path (function attributes, allocator)
     # ---- device-resident timing (value)
     sync_all()
@@ -323,7 +344,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        run_trajectory(sampler, prior, dev_in, NS)
+        run_trajectory(hot, dev_in, NS)
     e1.record()
     sync_all()
     clk = clocks.stop()
@@ -331,12 +352,12 @@ def main():
     launches_eager = ops.LAUNCHES - l0
     # ---- end-to-end through the public API: pinned host inputs -> device, result -> host, every step
     sync_all()
-    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "llm" or prior is not None)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
         cur = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        out = run_trajectory(sampler, prior, cur, NS)
+        out = run_trajectory(hot, cur, NS)
         v0 = torch.cuda.Event(enable_timing=True)
         v0.record()
         img = vae.decode(out)                                    # sdxl_pipeline.py:859-871: latents -> (B,3,8L,8L) images
@@ -364,7 +385,7 @@ def main():
     whole_frac = step_flops / (unet_step_ms * 1e-3) / (pk["sustained"] * 1e12)
     # launches: graph replays re-issue the captured kernels
     per_forward = getattr(sampler, "launches_per_forward", None)
-    by = profile_dominant_kernel(unet, sampler, dev_in, B)
+    by = profile_dominant_kernel(unet, sampler, dev_in, B, hot.ip_context(dev_in["ctx"], dev_in["llm"]))
     n_forward_kernels = sum(d["n"] * ops._KERNELS_PER_CALL.get(k, 1) for k, d in by.items())
     gpu_launches = launches_eager + (0 if args.no_graph else args.steps * NS * n_forward_kernels)
     tc = dict(ms=0.0, flops=0.0, n=0, bytes=0.0)
@@ -388,7 +409,7 @@ def main():
                            cuda_graph=not args.no_graph, residual_stream="fp32"),
                unet_step_ms=unet_step_ms, unet_tensor_frac=whole_frac, clocks=clk,
                e2e=dict(value=e2e_value, unit="images/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                        includes="H2D of the conditioning + noise, 50-step trajectory, VAE decode to fp32 images, D2H of the images",
+                        includes="H2D of the text conditioning + LLM embedding + noise, (prior,) image projector -> IP tokens, 50-step trajectory, VAE decode to fp32 images, D2H of the images",
                         vae_decode_and_readback_ms=ms_decode),
                gpu_launches=int(gpu_launches), roofline=roof)
     if not args.no_cpu_baseline:

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libia2p_sm100a.so")
+LIB_PATH = os.environ.get("IA2P_LIB_OVERRIDE") or os.path.join(_HERE, "libia2p_sm100a.so")   # override: A/B experiment builds only
 
 F32, BF16, F16 = 0, 1, 2
 EPI_NONE, EPI_GEGLU = 0, 1

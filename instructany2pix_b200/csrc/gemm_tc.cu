@@ -17,6 +17,10 @@
 
 #include "common.cuh"
 
+#ifndef IA2P_MAX_STAGES
+#define IA2P_MAX_STAGES 6   // smem ring depth cap (experiments: make variant NAME=.. DEFS=-DIA2P_MAX_STAGES=..)
+#endif
+
 namespace ia2p {
 
 struct TapEntry {
@@ -123,7 +127,7 @@ struct TcCfg {
   static constexpr int NBF = (EPI == 2) ? 4 : 1, NBH = (EPI == 2) ? 2 : 1;       // staging ring depth per half-group
   static constexpr int EPI_BYTES = EPI ? 2 * (NBF * EPI_F_BYTES + NBH * EPI_H_BYTES) : 0;
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - BAR_BYTES - EPI_BYTES;
-  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > IA2P_MAX_STAGES ? IA2P_MAX_STAGES : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int STAGE_OFF = STAGES * STAGE_BYTES + BAR_BYTES;            // epilogue staging, from smem_base
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_BYTES;

@@ -4,6 +4,9 @@ What the reference does per edit request once the LLM / prompt encoders have pro
 reference code, SURVEY 8 "out of scope"), and which call below replaces it:
 
   pipeline.py:313-316   y = self.model.generate_diffusion(...)                      -> ``prior.generate_diffusion`` (B200Prior)
+  pipeline.py:324-326   latent_la = mix(base, llm, y / |y| * 20); / |.| * norm       -> ``ip_context`` (caller arithmetic on 1024-vectors)
+  ip_adapter.py:171-209 image_proj_model(embeds) / (zeros) -> 4 IP tokens            -> ``image_proj.get_image_embeds`` (B200ImageProj)
+  ip_adapter.py:336-342 cat([text, ip_tokens], dim=1), [negative ; positive]         -> ``ip_context``
   pnp_pipeline.py:195   latents = vae.encode(image).latent_dist.sample() * sf       -> ``vae.encode``
   pnp_pipeline.py:251   DDIM inversion, N UNet forwards, no CFG                      -> ``sampler.invert``
   pipeline.py:332-336   polar_intrtpolate(latent_inv, randn_like(latent_inv), alpha) -> ``sampler.start_latent``
@@ -20,8 +23,8 @@ from .sampler import B200Sampler
 
 
 class B200HotPath:
-    def __init__(self, unet, vae, scheduler=None, prior=None, use_cuda_graph=True):
-        self.unet, self.vae, self.prior = unet, vae, prior
+    def __init__(self, unet, vae, scheduler=None, prior=None, use_cuda_graph=True, image_proj=None):
+        self.unet, self.vae, self.prior, self.image_proj = unet, vae, prior, image_proj
         self.sampler = B200Sampler(unet, scheduler=scheduler, use_cuda_graph=use_cuda_graph)
 
     @torch.no_grad()
@@ -37,6 +40,27 @@ class B200HotPath:
         z = self.sampler.generate(z_t, ctx_cfg, added_cfg, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale)
         img = self.vae.decode(z)
         return (img, z) if return_latents else img
+
+    @torch.no_grad()
+    def ip_context(self, text_ctx_cfg, llm_embed, prior_embed=None, base_embed=None, h=(0.0, 0.4, 1.0), norm=20.0,
+                   mode="global"):
+        """The conditioning hand-over of an edit request: text_ctx_cfg (2B, 77, D) = [negative ; positive] prompt embeddings,
+        llm_embed (B, 1024) = the LLM's image embedding, prior_embed (B, 1024) = ``generate_diffusion`` output (None: the
+        LLM embedding is used as it is), base_embed (B, 1024) optional.  Mixes like pipeline.py:324-326
+        (``base h0 + llm h1 + y/|y| 20 h2``, renormalised to ``norm``; plain torch on B x 1024 numbers, the caller's
+        arithmetic in the reference), projects to IP tokens with ``B200ImageProj`` (uncond = projector(zeros)) and appends them:
+        -> (2B, 77 + T, D) for ``B200Sampler.generate``."""
+        B = llm_embed.shape[0]
+        e = llm_embed.reshape(B, -1).float()
+        if prior_embed is not None:
+            y = prior_embed.reshape(B, -1).float().to(e.device)
+            e = e * h[1] + y / y.norm(dim=-1, keepdim=True) * 20.0 * h[2]
+            if base_embed is not None:
+                e = e + base_embed.reshape(B, -1).float() * h[0]
+        e = e / e.norm(dim=-1, keepdim=True) * norm
+        cond, uncond = self.image_proj.get_image_embeds(clip_image_embeds=e, mode=mode)
+        ip = torch.cat([uncond, cond], dim=0).to(text_ctx_cfg.dtype)
+        return torch.cat([text_ctx_cfg, ip], dim=1).contiguous()
 
     @torch.no_grad()
     def generate(self, latents, ctx_cfg, added_cfg, num_inference_steps=50, guidance_scale=10.0):

@@ -125,9 +125,13 @@ class ImageProjModel(nn.Module):
         return self.norm(t)
 
 
-def get_image_embeds(image_proj_model, clip_image_embeds, mode="global", scale_g=1.0, scale_l=1.0):
-    """IPAdapter.get_image_embeds with ``clip_image_embeds`` given and no local crop
-    (ip_adapter.py:171-209): local := zeros, uncond := projector(zeros)."""
-    local = torch.zeros_like(clip_image_embeds)
-    e = torch.stack([clip_image_embeds, local], dim=1)
+def get_image_embeds(image_proj_model, clip_image_embeds=None, clip_image_embeds_local=None, mode="global", scale_g=1.0,
+                     scale_l=1.0):
+    """IPAdapter.get_image_embeds with the CLIP embeddings given (ip_adapter.py:171-209): a missing crop := zeros,
+    uncond := projector(zeros) with the default scales.  Pinned by tests/golden/image_proj.npz (k64/gie_*)."""
+    if clip_image_embeds is None:
+        clip_image_embeds = torch.zeros_like(clip_image_embeds_local)
+    elif clip_image_embeds_local is None:
+        clip_image_embeds_local = torch.zeros_like(clip_image_embeds)
+    e = torch.stack([clip_image_embeds, clip_image_embeds_local], dim=1)
     return image_proj_model(e, mode=mode, scales=[scale_g, scale_l]), image_proj_model(torch.zeros_like(e), mode=mode)

@@ -52,6 +52,14 @@ def gen_attention():
     np.savez_compressed(os.path.join(OUT, "attn.npz"), **out)
 
 
+IMAGE_PROJ_K64 = dict(cross=128, clip=64)
+IMAGE_PROJ_MODES = [("global", [1.0, 1.0]), ("local", [1.0, 0.5]), ("both", [0.7, 0.25])]
+
+
+def image_proj_k64_inputs():
+    return synth_input("image_proj/k64/e", (3, IMAGE_PROJ_K64["clip"])), synth_input("image_proj/k64/el", (3, IMAGE_PROJ_K64["clip"]))
+
+
 def gen_image_proj():
     Ref = ref_shims.extract_source("instructany2pix/diffusion/ip_adapter/ip_adapter.py", "ImageProjModel")
     m = Ref(cross_attention_dim=64, clip_embeddings_dim=48, clip_extra_context_tokens=4)
@@ -61,6 +69,26 @@ def gen_image_proj():
     with torch.no_grad():
         for mode, scales in [("global", [1.0, 1.0]), ("local", [1.0, 0.5]), ("both", [0.7, 0.25])]:
             out[mode] = m(e.clone(), mode, scales=scales).numpy()
+    # second configuration with kernel-friendly widths (K multiple of 32) for the GPU drop-in (B200ImageProj), non-zero
+    # raw_embed, plus IPAdapter.get_image_embeds itself (ip_adapter.py:171-209, a method: extracted and run with a stand-in
+    # ``self``; the reference casts the embeddings to fp16 there, so the module is run in fp16 like the reference does)
+    m2 = Ref(cross_attention_dim=IMAGE_PROJ_K64["cross"], clip_embeddings_dim=IMAGE_PROJ_K64["clip"], clip_extra_context_tokens=4)
+    m2.load_state_dict(synth_state_dict(m2, 2))
+    e2, e2l = image_proj_k64_inputs()
+    with torch.no_grad():
+        for mode, scales in IMAGE_PROJ_MODES:
+            out["k64/" + mode] = m2(torch.stack([e2, e2l], 1), mode, scales=scales).numpy()
+        import types
+        from PIL import Image
+        gie = ref_shims.extract_source("instructany2pix/diffusion/ip_adapter/ip_adapter.py", "get_image_embeds", {"Image": Image})
+        import contextlib
+        import io
+        fake = types.SimpleNamespace(image_proj_model=m2.half(), device="cpu")
+        with contextlib.redirect_stdout(io.StringIO()):          # the reference prints a comparison tensor
+            c, u = gie(fake, clip_image_embeds=e2, mode="global", scale_g=1.0, scale_l=1.0)
+            c2, u2 = gie(fake, clip_image_embeds=e2, clip_image_embeds_local=e2l, mode="both", scale_g=1.0, scale_l=0.4)
+        out["k64/gie_cond"], out["k64/gie_uncond"] = c.float().numpy(), u.float().numpy()
+        out["k64/gie_both_cond"], out["k64/gie_both_uncond"] = c2.float().numpy(), u2.float().numpy()
     np.savez_compressed(os.path.join(OUT, "image_proj.npz"), **out)
 
 
