@@ -16,8 +16,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_dev_ok[64];     // 0 unknown, 1 ok, -1 bad
-static int g_sm_count[64];
+static std::atomic<int> g_dev_ok[64];     // 0 unknown, 1 ok, -1 bad (written after g_sm_count: a reader that sees != 0 sees the count)
+static std::atomic<int> g_sm_count[64];
 
 static int query_device(int dev) {
   if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return IA2P_E_DEVICE; }
@@ -25,8 +25,8 @@ static int query_device(int dev) {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, dev);
     if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return IA2P_E_DEVICE; }
-    g_sm_count[dev] = prop.multiProcessorCount;
-    g_dev_ok[dev] = (prop.major == 10) ? 1 : -1;
+    g_sm_count[dev].store(prop.multiProcessorCount);
+    g_dev_ok[dev].store((prop.major == 10) ? 1 : -1);
     if (g_dev_ok[dev] < 0) set_error("device %d is sm_%d%d; this library only runs on sm_100 (B200)", dev, prop.major, prop.minor);
   }
   if (g_dev_ok[dev] < 0) {

@@ -330,11 +330,7 @@ static int launch_cross(const void* q, int64_t ldq, const void* kt, const void* 
                         const void* vi, int64_t ldkv_ip, int n_ip, float ip_scale, void* out, int64_t ldo, int64_t batch,
                         int64_t n_q, int heads, float scale, cudaStream_t st) {
   constexpr int smem = 2 * 128 * 128 + 2 * (T1 + T2) * 128;
-  static bool done = false;
-  if (!done) {
-    IA2P_CUDA(cudaFuncSetAttribute(cross_attn_kernel<T1, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    done = true;
-  }
+  IA2P_ONCE_PER_DEVICE(IA2P_CUDA(cudaFuncSetAttribute(cross_attn_kernel<T1, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
   // query tiles per (batch, head) are split over the fewest CTAs that still fill the GPU (~3 CTAs per SM): K/V loads amortise
   const int n_qtiles = (int)((n_q + 127) / 128);
   int split = n_qtiles;
@@ -380,11 +376,7 @@ extern "C" int ia2p_flash_self_attn_bf16(const void* q, const void* k, const voi
   if (!use_legacy_attn())
     return launch_fa_tc(q, k, v, ld, out, ldo, batch, n_tokens, heads, softmax_scale, static_cast<cudaStream_t>(stream));
   constexpr int smem = 128 * 128 + 4 * 64 * 128;
-  static bool done = false;
-  if (!done) {
-    IA2P_CUDA(cudaFuncSetAttribute(flash_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    done = true;
-  }
+  IA2P_ONCE_PER_DEVICE(IA2P_CUDA(cudaFuncSetAttribute(flash_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
   const dim3 grid((unsigned)((n_tokens + 127) / 128), (unsigned)heads, (unsigned)batch);
   flash_self_attn_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), ld,

@@ -361,12 +361,9 @@ int launch_fa_tc(const void* q, const void* k, const void* v, int64_t ld, void* 
   if (int e = fa_make_map(&maps.q, q, heads * 64, ld, n_tokens, batch)) return e;
   if (int e = fa_make_map(&maps.k, k, heads * 64, ld, n_tokens, batch)) return e;
   if (int e = fa_make_map(&maps.v, v, heads * 64, ld, n_tokens, batch)) return e;
-  static bool done = false;
-  if (!done) {
-    IA2P_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
-    IA2P_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    done = true;
-  }
+  IA2P_ONCE_PER_DEVICE(
+      IA2P_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
+      IA2P_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
   const dim3 grid((unsigned)((n_tokens + 127) / 128), (unsigned)heads, (unsigned)batch);
   launch_pdl(fa_tc_kernel, dim3(grid), dim3(192), kFaSmemBytes, st, maps, static_cast<__nv_bfloat16*>(out), ldo, (int)n_tokens,
                                                 softmax_scale * 1.4426950408889634f);

@@ -3,6 +3,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 
 #include "../../include/ia2p.h"
@@ -30,6 +32,19 @@ int sm_count();
   } while (0)
 #define IA2P_LAUNCH_CHECK() IA2P_CUDA(cudaGetLastError())
 bool pdl_enabled();                        // IA2P_PDL=1 enables programmatic dependent launch (off by default, see below)
+// Kernel function attributes (dynamic shared-memory limit, carve-out) belong to the DEVICE: set them once per device this
+// process launches on, not once per process.  `stmts` may use IA2P_CUDA (returns the error code from the enclosing function).
+#define IA2P_ONCE_PER_DEVICE(stmts)                                            \
+  do {                                                                         \
+    static std::atomic<unsigned long long> _done{0};                           \
+    int _dev = 0;                                                              \
+    IA2P_CUDA(cudaGetDevice(&_dev));                                           \
+    const unsigned long long _bit = 1ull << (_dev & 63);                       \
+    if (!(_done.load(std::memory_order_acquire) & _bit)) {                     \
+      stmts;                                                                   \
+      _done.fetch_or(_bit, std::memory_order_release);                         \
+    }                                                                          \
+  } while (0)
 
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialisation attribute
 template <typename... KArgs, typename... Args>

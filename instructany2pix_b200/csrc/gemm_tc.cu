@@ -997,11 +997,7 @@ static bool tail_split_enabled() {
 template <int BN, int CG, int EPI>
 static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, CG, EPI>;
-  static bool attr_done = false;   // benign race: idempotent
-  if (!attr_done) {
-    IA2P_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  IA2P_ONCE_PER_DEVICE(IA2P_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
   p.n_tiles = (p.N + BN - 1) / BN;
   const int units = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
   const int max_units = sm_count() / CG;
