@@ -28,12 +28,12 @@ constexpr int kFaTile = 128 * 128;                 // bytes: 128 rows x 64 bf16
 constexpr int kFaSmemTiles = kFaTile * (1 + 2 + 2);       // Q, K x2, V x2
 constexpr int kFaSmemBytes = kFaSmemTiles + 1024;  // barriers live in the alignment slack in front of the tiles
 constexpr float kRescaleThreshold = 8.0f;
-// What bounds this kernel (measured, tools/trace_attn.py + ncu): per 128 x 128 key block the softmax warps must read 64 KB of S
-// from TMEM (tcgen05.ld: 64 B/clk per SM -> 1024 cycles) and evaluate 16 384 exponentials on the 16 SFU lanes of the SM (1024
-// cycles), while the two MMAs need 512 cycles at head_dim 64: the tensor pipe cannot exceed ~50 %.  The kernel runs a block in
-// ~1 200 cycles per SM (two co-resident CTAs at ~2 400 each), i.e. ~85 % of that TMEM/SFU floor.  Tried and dropped because
-// they did not move it: bf16 packing by truncation instead of F2FP, and evaluating every 4th exp2 on the FMA pipe with a
-// polynomial (FlashAttention-4 style) -- the latter made the block slower (2 435 -> 2 751 cycles).
+// What bounds this kernel (measured, tools/trace_attn.py, tools/mmabench.cu, ncu): MMA ISSUE.  One tcgen05.mma (M 128, K 16) costs
+// max(94, N/2 + 38) cycles whatever it computes, so a 128 x 128 key block needs 4 x 102 (Q.K^T, N 128) + 8 x 94 (P.V, N 64) =
+// 1 163 cycles of the tensor pipe per CTA, 2 326 for the two co-resident CTAs; the kernel takes 2 435 (95 % of that floor).  The
+// softmax side (64 KB of S through tcgen05.ld, 16 384 exponentials on 16 SFU lanes: ~1 024 cycles per block and SM) is second,
+// which is why bf16 packing by truncation and evaluating every 4th exp2 on the FMA pipe (FlashAttention-4 style) did not help
+// (2 435 -> 2 751 cycles).  P.V cannot use a wider N (N = head_dim) nor more K per instruction (K = 16 for bf16).
 #ifdef IA2P_TC_TRACE
 #define IA2P_TRACE_BUF g_fa_trace
 __device__ unsigned long long* g_fa_trace = nullptr;           // debug build: counters of the CTAs with blockIdx.y == z == 0

@@ -247,6 +247,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint3
       : "memory");
 }
 
+// Multicast TMA load: the box lands at the SAME shared-memory offset in every CTA of `cta_mask` (cluster ranks) and completes
+// tx bytes on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+
 // TMA store (shared::cta -> global, bulk async-group completion) of one 4-D box; out-of-bounds parts of the box are clipped.
 __device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -352,6 +361,11 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same, arriving on the barrier at this offset in every CTA of `cta_mask` (single-CTA MMAs inside a cluster that shares operands).
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 // Arrive on an mbarrier when all tcgen05 ops previously issued by this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -51,6 +51,10 @@ struct TcParams {
   int ksplit, kb_per;
   float* ws;
   unsigned* flags;
+  // A-operand multicast (single-wave problems on the single-CTA kernel): `mc` CTAs of a cluster own consecutive n-tiles of the
+  // SAME row tile; each loads 1/mc of the 128 A rows per k-block (the a[] maps then carry the slice box) and multicasts it to
+  // all of them, so the L2 -> SM traffic of A drops by mc (host side: pick_mc / slice_box).
+  int mc;
   int trace_id;                    // debug build: launch id for the in-graph timeline
   // Weight prefetch hint (ia2p_tc_prefetch_hint): the NEXT tcgen05 launch's weight matrix.  Every CTA pulls its slice into L2
   // once its first tile's loads are under way, so the next kernel's first wave does not start on cold DRAM misses.
@@ -232,6 +236,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t mc = (CG == 1 && p.mc > 1) ? (uint32_t)p.mc : 1u;      // A-multicast cluster size
+  const uint32_t crank = (mc > 1) ? cluster_ctarank() : 0u;
   pdl_launch_dependents();
 #ifdef IA2P_TC_TRACE
   if (warp == 0) TRACE_PUT(0, gtime_ns());
@@ -251,7 +257,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);               // CG = 2: the leader expects BOTH CTAs' TMA bytes on its barrier
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), mc);             // multicast: a stage is free once EVERY CTA of the cluster has consumed it
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
@@ -264,7 +270,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();        // peer barriers must be initialised before remote arrives
+  if (CG == 2 || mc > 1) cluster_sync_all(); else __syncthreads();   // peer barriers must be initialised before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();                                                   // everything above overlapped the previous kernel's tail
@@ -289,6 +295,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint32_t phase = 0;
     TRACE_DECL(tr_wait_empty);
     bool pf_done = (p.pf_ptr == nullptr);
+    // multicast: first pixel of this CTA's slice inside the tile's (TB, TH, TW) box; rows are ordered (tb, th, tw)
+    const int mc_row0 = (int)crank * (128 / (int)mc);
+    const int mc_x = mc_row0 & ((1 << p.tw_log2) - 1);
+    const int mc_y = (mc_row0 >> p.tw_log2) & ((1 << p.th_log2) - 1);
+    const int mc_b = mc_row0 >> (p.tw_log2 + p.th_log2);
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
       const int m_tile = ti.m_unit * CG + (int)rank;    // may be == m_tiles for the odd tail: TMA zero-fills (batch coord OOB)
@@ -318,6 +329,14 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
               tma_load_4d_2sm(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
               tma_load_2d_2sm(a_dst + Cfg::A_BYTES, wm, full_bar(stage), t.wk0 + c * 64, n0);
+            } else if (mc > 1) {
+              // this CTA's slice of the A rows goes to every CTA of the cluster; the other slices arrive from the peers.  A
+              // peer's bytes may land before the arrive below (signed tx-count), never a phase early: the peer's stage is
+              // only freed by THIS CTA's multicast commit as well.
+              mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+              tma_load_4d_mc(a_dst + crank * (uint32_t)(Cfg::A_BYTES / (int)mc), am, full_bar(stage), c * 64, x0 + t.dx + mc_x,
+                             y0 + t.dy + mc_y, b0 + mc_b, (uint16_t)((1u << mc) - 1u));
+              tma_load_2d(a_dst + Cfg::A_BYTES, wm, full_bar(stage), t.wk0 + c * 64, n0);
             } else {
               mbar_arrive_expect_tx(full_bar(stage), stage_tx);
               tma_load_4d(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
@@ -382,7 +401,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             umma_commit_2sm_mc(empty_bar(stage), 3);             // frees this stage in BOTH CTAs
             if (kb == nkb - 1) umma_commit_2sm_mc(tfull_bar(buf), 3);
           } else {
-            umma_commit(empty_bar(stage));
+            if (mc > 1) umma_commit_mc(empty_bar(stage), (uint16_t)((1u << mc) - 1u));   // frees this stage in every CTA of the cluster
+            else umma_commit(empty_bar(stage));
             if (kb == nkb - 1) umma_commit(tfull_bar(buf));
           }
         }
@@ -875,7 +895,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (warp == 0) TRACE_PUT(8, gtime_ns());
 #endif
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();        // both CTAs done with TMEM / no remote arrive in flight
+  if (CG == 2 || mc > 1) cluster_sync_all(); else __syncthreads();   // all CTAs done with TMEM / no remote arrive or multicast in flight
   if (warp == 1) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -1025,7 +1045,9 @@ static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
     }
   }
   const int rem = units % max_units;
-  const bool can_split = p.ksplit == 1 && tail_split_enabled() && (BN % 64 == 0) && (!p.geglu || BN % 128 == 0) && (p.N % BN == 0);
+  IA2P_REQUIRE(p.mc <= 1 || (CG == 1 && p.ksplit == 1 && units <= max_units && p.n_tiles % p.mc == 0), IA2P_E_ARG,
+               "tc launch: A-multicast picked for a launch that cannot run it (internal)");
+  const bool can_split = p.ksplit == 1 && p.mc <= 1 && tail_split_enabled() && (BN % 64 == 0) && (!p.geglu || BN % 128 == 0) && (p.N % BN == 0);
   if (can_split && units > max_units && rem != 0 && 2 * rem <= max_units) {
     p.split = 2;
     p.full_items = units - rem;
@@ -1038,7 +1060,7 @@ static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = (CG == 1 && p.mc > 1) ? p.mc : CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1072,6 +1094,36 @@ static bool use_pair(int m_tiles, int num_kb, int64_t N, int bn) {
   if (pick_ksplit((int64_t)m_tiles * ((N + bn - 1) / bn), num_kb, bn) > 1) return false;   // split-K runs on the single-CTA kernel
   if (v == 0 && (int64_t)m_tiles * ((N + bn - 1) / bn) < 2 * sm_count()) return false;   // too few tiles to pair up
   return v == 2 || (v == 0 && num_kb > 12);
+}
+
+// A-operand multicast (TcParams::mc), OPT-IN (IA2P_GEMM_MC=2 | 4 = largest cluster): for problems that fit in ONE wave of
+// single-CTA tiles (few output rows: batch-1 512^2, a single interactive request) every row tile's A block is fetched by all
+// of its n-tiles; clusters of mc CTAs (consecutive n-tiles of one row tile) fetch each A block once and multicast it.  Needs
+// n_tiles % mc == 0 and all clusters co-resident (one CTA per SM: floor(SMs per GPC / mc) clusters per GPC; the cap below is
+// conservative).  Measured on B200 (tools/small_m_graph.py, profiles/README.md section 9): NO gain -- M 512 / 2048, N 1280,
+// K 5120: 33.6 / 39.1 us without, 34.2 / 40.0 us with clusters of 4 -- the few-row main loop is bound by MMA issue (>= 94
+// cycles per tcgen05.mma whatever its N) and by shared-memory bandwidth (every CTA still receives the whole A tile), not by the
+// L2 -> SM traffic multicast removes.  Hence off by default.
+static int pick_mc(int bn, int64_t m_tiles, int64_t N, int num_kb) {
+  const char* e = getenv("IA2P_GEMM_MC");                // read per call (tests toggle it); a few ns next to a launch
+  const int cap = (e != nullptr && (e[0] == '2' || e[0] == '4')) ? (e[0] - '0') : 1;
+  if (cap <= 1 || N % bn != 0 || use_pair((int)m_tiles, num_kb, N, bn)) return 1;
+  const int64_t n_tiles = N / bn, units = m_tiles * n_tiles;
+  if (units > sm_count() || pick_ksplit(units, num_kb, bn) > 1) return 1;
+  for (int mc = cap; mc >= 2; mc >>= 1) {
+    const int64_t resident = (mc == 4) ? (sm_count() / 18) * 4 * 4 : (sm_count() / 18) * 9 * 2;   // 8 GPCs x floor(18 / mc) clusters
+    if (n_tiles % mc == 0 && units <= resident) return mc;
+  }
+  return 1;
+}
+// shrink an A-operand pixel box {64, TW, TH, TB} (128 rows ordered (tb, th, tw)) to one of mc row slices
+static void slice_box(uint32_t* box, int mc) {
+  int rows = 128 / mc;
+  for (int d = 1; d < 4; ++d) {
+    const uint32_t take = box[d] < (uint32_t)rows ? box[d] : (uint32_t)rows;
+    rows /= (int)take;
+    box[d] = take;
+  }
 }
 
 // fp32 outputs go through the TMA-store epilogue (EPI = 1); IA2P_GEMM_EPI=0 forces the register-store epilogue (experiments)
@@ -1236,10 +1288,12 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
   const int bn = pick_block_n(N, geglu, (M + 127) / 128, (int)((K1 + K2) / 64));
   TcMaps maps;
   TcParams p{};
+  p.mc = pick_mc(bn, (M + 127) / 128, N, (int)((K1 + K2) / 64));
+  uint32_t box[4] = {64, 128, 1, 1};
+  slice_box(box, p.mc);
   {
     const uint64_t dims[4] = {(uint64_t)K1, (uint64_t)M, 1, 1};
     const uint64_t str[4] = {1, (uint64_t)lda, (uint64_t)lda * (uint64_t)M, (uint64_t)lda * (uint64_t)M};
-    const uint32_t box[4] = {64, 128, 1, 1};
     if (int e = make_map(&maps.a[0], A, 4, dims, str, box)) return e;
     maps.a[1] = maps.a[0]; maps.a[2] = maps.a[0]; maps.a[3] = maps.a[0];
   }
@@ -1248,7 +1302,6 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
   if (A2 != nullptr) {
     const uint64_t dims[4] = {(uint64_t)K2, (uint64_t)M, 1, 1};
     const uint64_t str[4] = {1, (uint64_t)lda2, (uint64_t)lda2 * (uint64_t)M, (uint64_t)lda2 * (uint64_t)M};
-    const uint32_t box[4] = {64, 128, 1, 1};
     if (int e = make_map(&maps.a[1], A2, 4, dims, str, box)) return e;
     p.taps[1] = TapEntry{1, 0, 0, (int16_t)(K2 / 64), (int32_t)K1};
     p.ntaps = 2;
@@ -1300,7 +1353,9 @@ static int conv3x3_impl(const void* x, int64_t B, int64_t H, int64_t W, int64_t 
 
   TcMaps maps;
   TcParams p{};
-  const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+  p.mc = pick_mc(bn, (Wo / TW) * (Ho / TH) * ((B + TB - 1) / TB), Cout, (int)(Ktot / 64));
+  uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+  slice_box(box, p.mc);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   int nt = 0;
   if (stride == 1) {
@@ -1388,13 +1443,16 @@ extern "C" int ia2p_conv_up2x_nhwc_bf16(const void* x, int64_t B, int64_t H, int
   const int TB = 128 / (TW * TH);
   const int64_t Ktot = 4 * Cin;
   const int bn = pick_block_n(Cout, false, (W / TW) * (H / TH) * ((B + TB - 1) / TB), (int)(Ktot / 64));
-  const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+  const int mc = pick_mc(bn, (W / TW) * (H / TH) * ((B + TB - 1) / TB), Cout, (int)(Ktot / 64));
+  uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+  slice_box(box, mc);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(w4);
   for (int par = 0; par < 4; ++par) {
     const int py = par >> 1, px = par & 1;
     TcMaps maps;
     TcParams p{};
+    p.mc = mc;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)(W * Cin), (uint64_t)(H * W * Cin)};
     if (int e = make_map(&maps.a[0], xb, 4, dims, str, box)) return e;

@@ -92,12 +92,18 @@ def test_gemm_every_tile_width(bn, M, monkeypatch):
     assert rel(out, F.layer_norm(t, (N,), ln.weight, ln.bias, 1e-5) @ w3.float().t()) < 8e-3
 
 
-@pytest.mark.parametrize("kind", ["plain", "fp32_ln", "res_ring", "geglu", "conv", "conv_res"])
-def test_split_k_for_few_row_problems(kind, monkeypatch):
-    """(opt-in path, off by default: see ops.USE_SPLITK) fewer tiles than half the SMs -> every tile is computed by several CTAs over disjoint k-ranges; partials are summed in a
-    fixed order before the normal epilogue: same results as the one-CTA-per-tile path, bit-reproducible run to run."""
-    from instructany2pix_b200.packing import interleave_geglu, pack_conv3x3
-    monkeypatch.setattr(ops, "USE_SPLITK", True)
+@pytest.mark.parametrize("path", ["multicast", "splitk"])
+@pytest.mark.parametrize("kind", ["plain", "fp32_ln", "res_ring", "geglu", "conv", "conv_res", "conv_s2", "conv_8x8", "up2x", "kcat"])
+def test_few_row_problems(kind, path, monkeypatch):
+    """Problems that fit in one wave of tiles (batch-1 512^2, single requests), two opt-in paths (both measured, neither faster than
+    one narrow tile per CTA: DESIGN.md).  "multicast" (IA2P_GEMM_MC): clusters of 2 / 4
+    CTAs share each A block through TMA multicast (plain rows, 16x8 / 8x8x2 / 32x4 pixel boxes, parity-decimated stride-2 maps,
+    two K-concatenated sources).  "splitk" (ops.USE_SPLITK): every tile is computed by several CTAs over disjoint
+    k-ranges and the partials are summed in a fixed order.  Both: same results as the reference, bit-reproducible run to run."""
+    from instructany2pix_b200.packing import interleave_geglu, pack_conv3x3, pack_conv3x3_up2x
+    monkeypatch.setattr(ops, "USE_SPLITK", path == "splitk")
+    if path == "multicast":
+        monkeypatch.setenv("IA2P_GEMM_MC", "4")
     if kind == "plain":
         a, w = rnd(384, 2560), rnd(1280, 2560, scale=2560 ** -0.5)
         f = lambda: ops.gemm(a, w)
@@ -118,6 +124,23 @@ def test_split_k_for_few_row_problems(kind, monkeypatch):
         f = lambda: ops.gemm(a, wi, bias=bi, geglu=True)
         h = a.float() @ w.float().t() + b
         ref, tol = h[:, :1280] * F.gelu(h[:, 1280:]), TOL
+    elif kind == "kcat":
+        a, a2, w = rnd(512, 640), rnd(512, 320), rnd(1280, 960, scale=960 ** -0.5)
+        f = lambda: ops.gemm(a, w, a2=a2)
+        ref, tol = torch.cat([a, a2], 1).float() @ w.float().t(), TOL
+    elif kind == "conv_s2":
+        x, w = rnd(2, 32, 32, 128), rnd(512, 128, 3, 3, scale=(9 * 128) ** -0.5)
+        f = lambda: ops.conv3x3(x, pack_conv3x3(w), 512, stride=2)
+        ref, tol = _conv_ref(x, w, 2), TOL
+    elif kind == "conv_8x8":
+        x, w = rnd(3, 8, 8, 128), rnd(512, 128, 3, 3, scale=(9 * 128) ** -0.5)     # tile = 2 images x 8 x 8, last one half empty
+        f = lambda: ops.conv3x3(x, pack_conv3x3(w), 512)
+        ref, tol = _conv_ref(x, w), TOL
+    elif kind == "up2x":
+        x, w, b = rnd(1, 32, 32, 128), rnd(256, 128, 3, 3, scale=(9 * 128) ** -0.5), rnd(256, dtype=torch.float32)
+        f = lambda: ops.conv_up2x(x, pack_conv3x3_up2x(w), 256, bias=b)
+        up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+        ref, tol = F.conv2d(up, w.float(), b, padding=1).permute(0, 2, 3, 1), 3e-3
     else:
         x, w = rnd(2, 16, 16, 640), rnd(1280, 640, 3, 3, scale=(9 * 640) ** -0.5)
         res = rnd(2, 16, 16, 1280, dtype=torch.float32) if kind == "conv_res" else None
