@@ -126,13 +126,15 @@ int ia2p_gemm_bf16(const void* A, int64_t lda, int64_t K1, const void* A2, int64
  * statistics pass over it.  Tiles follow the output pixel order (128 consecutive pixels; needs H*W % 128 == 0 to be usable by
  * GroupNorm); conv_up2x writes 4 segments, one per output parity. */
 
-/* Split-K workspace for the tensor-core kernels (optional).  Problems with few output rows (fewer 128 x BLOCK_N tiles than half
+/* Split-K workspace for the tensor-core kernels (EXPERIMENT builds only: ia2p_tc_features() & 1; the shipped library accepts and
+ * ignores it).  Problems with few output rows (fewer 128 x BLOCK_N tiles than half
  * the SMs: batch-1 512^2, single interactive requests) are otherwise bound by the latency of one tile's K loop; with a workspace
  * every tile is computed by up to 8 CTAs over disjoint k-ranges, the partial accumulators meet in `workspace` and split 0 adds them
  * in a fixed order (bit-reproducible) before the normal epilogue.  workspace: device memory, 256-byte aligned,
  * ia2p_tc_workspace_bytes() bytes, its first 16 KB ZEROED once by the caller (tile arrival counters, self-resetting); it stays
  * registered for this host thread until replaced (NULL clears) and must only be used by ONE stream at a time. */
 int64_t ia2p_tc_workspace_bytes(void);
+int ia2p_tc_features(void);   /* experiment paths compiled into this build: bit 0 split-K, bit 1 A-operand multicast (0 in the shipped library) */
 int ia2p_set_tc_workspace(void* workspace, int64_t bytes);
 
 /* One-shot hint for the NEXT ia2p_gemm_* / ia2p_conv* call made by this host thread: that launch also pulls `bytes` of

@@ -39,6 +39,7 @@ SIGNATURES = {
                            _p, _l, _p, _p, _p, _l, _p, _f, _p], _i),
     "ia2p_gemm_ln_parts": ([_l, _l, _l], _l),
     "ia2p_tc_workspace_bytes": ([], _l),
+    "ia2p_tc_features": ([], _i),
     "ia2p_set_tc_workspace": ([_p, _l], _i),
     "ia2p_conv_colstats_tiles": ([_l, _l, _l], _l),
     "ia2p_tc_prefetch_hint": ([_p, _l], _i),

@@ -354,6 +354,9 @@ static int launch_cross(const void* q, int64_t ldq, const void* kt, const void* 
 namespace ia2p {
 int launch_fa_tc(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int64_t batch,
                  int64_t n_tokens, int heads, float softmax_scale, cudaStream_t st);
+int launch_xattn_tc(const void* q, int64_t ldq, const void* kt, const void* vt, int64_t ldkv, int n_text, const void* ki,
+                    const void* vi, int64_t ldkv_ip, int n_ip, float ip_scale, void* out, int64_t ldo, int64_t batch, int64_t n_q,
+                    int heads, float scale, cudaStream_t st, bool* handled);
 }
 using namespace ia2p;
 
@@ -395,6 +398,13 @@ extern "C" int ia2p_decoupled_cross_attn_bf16(const void* q, int64_t ldq, const 
   IA2P_REQUIRE(n_ip == 0 || (k_ip && v_ip), IA2P_E_ARG, "cross_attn: k_ip/v_ip required when n_ip > 0");
   IA2P_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && (n_ip == 0 || ldkv_ip % 8 == 0), IA2P_E_ALIGN, "cross_attn: leading dims must be multiples of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool legacy_cross = [] { const char* e = getenv("IA2P_XATTN_IMPL"); return e != nullptr && e[0] == 'm'; }();   // A/B only
+  if (!use_legacy_attn() && !legacy_cross) {                  // tcgen05 kernel (xattn_tc.cu) whenever all keys fit 128 columns
+    bool handled = false;
+    const int e = launch_xattn_tc(q, ldq, k_text, v_text, ldkv, n_text, k_ip, v_ip, ldkv_ip, n_ip, ip_scale, out, ldo, batch, n_q, heads,
+                                  softmax_scale, st, &handled);
+    if (e != 0 || handled) return e;
+  }
   const int t1 = n_text <= 80 ? 80 : (n_text <= 96 ? 96 : 128);
 #define IA2P_CROSS(T1_, T2_) \
   return launch_cross<T1_, T2_>(q, ldq, k_text, v_text, ldkv, n_text, k_ip, v_ip, ldkv_ip, n_ip, ip_scale, out, ldo, batch, n_q, heads, softmax_scale, st)

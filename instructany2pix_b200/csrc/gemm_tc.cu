@@ -17,6 +17,11 @@
 
 #include "common.cuh"
 
+// Two few-row experiments live behind compile-time switches and are NOT part of the shipped library (make variant
+// DEFS="-DIA2P_WITH_SPLITK -DIA2P_WITH_MC"): split-K through an L2 workspace and A-operand TMA multicast in clusters.  Both
+// were measured slower than / equal to one narrow tile per CTA (profiles/README.md section 9), and merely compiling their
+// run-time branches into the kernel cost the batch-1 512^2 step 7 % (14.0 vs 13.0 ms, same box): hence compiled out.
+// ia2p_tc_features() reports what a build contains (bit 0 split-K, bit 1 multicast).
 #ifndef IA2P_MAX_STAGES
 #define IA2P_MAX_STAGES 6   // smem ring depth cap (experiments: make variant NAME=.. DEFS=-DIA2P_MAX_STAGES=..)
 #endif
@@ -236,7 +241,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef IA2P_WITH_MC
   const uint32_t mc = (CG == 1 && p.mc > 1) ? (uint32_t)p.mc : 1u;      // A-multicast cluster size
+#else
+  constexpr uint32_t mc = 1u;
+#endif
   const uint32_t crank = (mc > 1) ? cluster_ctarank() : 0u;
   pdl_launch_dependents();
 #ifdef IA2P_TC_TRACE
@@ -281,7 +290,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
   // tile walk: CG = 2 steps over tile PAIRS (two consecutive m-tiles); this CTA owns m_tile = 2 * pair + rank
   const int total_tiles = p.total_items;
+#ifdef IA2P_WITH_SPLITK                                          // experiment builds only (see the note at IA2P_WITH_SPLITK below)
   const bool splitk = (CG == 1) && p.ksplit > 1;                // one (tile, k-range) item per CTA
+#else
+  constexpr bool splitk = false;
+#endif
   const int unit0 = splitk ? (int)blockIdx.x / p.ksplit : (int)blockIdx.x / CG;
   const int unit_step = splitk ? (1 << 30) : (int)gridDim.x / CG;
   const int sidx = splitk ? (int)blockIdx.x % p.ksplit : 0;
@@ -982,6 +995,9 @@ static thread_local void* g_ws_ptr = nullptr;
 static thread_local long long g_ws_bytes = 0;
 constexpr long long kWsFlagBytes = 16384;
 static bool splitk_enabled() {
+#ifndef IA2P_WITH_SPLITK
+  return false;
+#endif
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("IA2P_GEMM_SPLITK");          // experiments only: 0 disables
@@ -1105,6 +1121,9 @@ static bool use_pair(int m_tiles, int num_kb, int64_t N, int bn) {
 // cycles per tcgen05.mma whatever its N) and by shared-memory bandwidth (every CTA still receives the whole A tile), not by the
 // L2 -> SM traffic multicast removes.  Hence off by default.
 static int pick_mc(int bn, int64_t m_tiles, int64_t N, int num_kb) {
+#ifndef IA2P_WITH_MC
+  return 1;
+#endif
   const char* e = getenv("IA2P_GEMM_MC");                // read per call (tests toggle it); a few ns next to a launch
   const int cap = (e != nullptr && (e[0] == '2' || e[0] == '4')) ? (e[0] - '0') : 1;
   if (cap <= 1 || N % bn != 0 || use_pair((int)m_tiles, num_kb, N, bn)) return 1;
@@ -1221,6 +1240,17 @@ extern "C" int ia2p_debug_set_trace(void* dev_buffer) {       // debug build onl
   return (int)cudaMemcpyToSymbol(g_tc_trace, &p, sizeof(p));
 }
 #endif
+
+extern "C" int ia2p_tc_features(void) {
+  int f = 0;
+#ifdef IA2P_WITH_SPLITK
+  f |= 1;
+#endif
+#ifdef IA2P_WITH_MC
+  f |= 2;
+#endif
+  return f;
+}
 
 extern "C" int64_t ia2p_tc_workspace_bytes(void) { return 64ll << 20; }
 

@@ -296,7 +296,8 @@ def layernorm(x, gamma, beta, eps, out_dtype=None):
 # library before every tc launch made through this module (a thread-local pointer on the library side; re-registering is ~ns)
 # Measured on B200 (tools/small_m.py, small_m_timeline.py; M 512, N 1280, K 5120): the k-loop shrinks 25 -> 9 us with 4 splits, but
 # the hand-over (+6 us), the fix-up reads (+8 us) and the now fully exposed 128 x 256 epilogue (+13 us) make the launch SLOWER
-# (37 vs 29 us; c2 step 13.9 vs 13.4 ms) than one narrow tile per CTA.  Kept opt-in (IA2P_GEMM_SPLITK=1) for the next round.
+# (37 vs 29 us; c2 step 13.9 vs 13.4 ms) than one narrow tile per CTA.  Opt-in (IA2P_GEMM_SPLITK=1) AND only present in experiment
+# builds of the library (ia2p_tc_features() & 1): the shipped kernel has the path compiled out (its branches cost c2 7 %).
 USE_SPLITK = os.environ.get("IA2P_GEMM_SPLITK", "0") == "1"
 _TC_WS = {}
 

@@ -118,7 +118,20 @@ def bench_attn():
     kvt = torch.randn(B * 77, 2 * heads * 64, device=dev).to(BF)
     kvi = torch.randn(B * 4, 2 * heads * 64, device=dev).to(BF)
     ms = timeit(lambda i: ops.cross_attn(q, kvt, 77, kvi, 4, 1.0, B, N, heads))
-    print(f"cross-attn lvl2: {ms * 1e3:8.1f} us  ({(2 * q.numel() * 2) / ms / 1e6:7.1f} GB/s of Q read + O write)")
+    print(f"cross-attn lvl2: {ms * 1e3:8.1f} us  ({(2 * q.numel() * 2) / ms / 1e6:7.1f} GB/s of Q read + O write)  [eager launches: host-bound]")
+    for name, B, N, heads in [("lvl2", 8, 1024, 20), ("lvl1", 8, 4096, 10), ("c2 lvl2", 2, 256, 20)]:
+        qs = [torch.randn(B * N, heads * 64, device=dev).to(BF) for _ in range(8)]       # > L2 at the c3 shapes
+        kvt = torch.randn(B * 77, 2 * heads * 64, device=dev).to(BF)
+        kvi = torch.randn(B * 4, 2 * heads * 64, device=dev).to(BF)
+        outs = [torch.empty_like(t) for t in qs]
+        ops.cross_attn(qs[0], kvt, 77, kvi, 4, 1.0, B, N, heads, out=outs[0])
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for t, o in zip(qs, outs):
+                ops.cross_attn(t, kvt, 77, kvi, 4, 1.0, B, N, heads, out=o)
+        ms = timeit(lambda i: g.replay(), iters=10) / len(qs)
+        print(f"cross-attn {name} in a CUDA graph: {ms * 1e3:8.1f} us  ({(2 * qs[0].numel() * 2) / ms / 1e6:7.1f} GB/s of Q read + O write)")
 
 
 def bench_norm():
