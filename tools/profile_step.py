@@ -23,7 +23,7 @@ unet, _ = bench.build_models(dev, False)
 host = bench.host_inputs(B, L, 1000)
 d = {k: v.to(dev) for k, v in host.items()}
 added = dict(text_embeds=d["pooled"], time_ids=d["tid"])
-kv = unet.context_kv(d["ctx"])
+kv = unet.context_kv(torch.cat([d["ctx"], torch.randn(2 * B, 4, 2048, device=dev).to(d["ctx"].dtype)], 1))   # 77 text + 4 IP tokens
 rb = unet.time_rowbias_table(torch.tensor([981.0]), added, 2 * B)[0].contiguous()
 x = d["lat"].float()
 from instructany2pix_b200 import ops

@@ -31,7 +31,7 @@ unet, _ = bench.build_models(dev, False)
 host = bench.host_inputs(B, L, 1000)
 dev_in = {k: v.to(dev) for k, v in host.items()}
 added = dict(text_embeds=dev_in["pooled"], time_ids=dev_in["tid"])
-kv = unet.context_kv(dev_in["ctx"])
+kv = unet.context_kv(torch.cat([dev_in["ctx"], torch.randn(2 * B, 4, 2048, device=dev).to(dev_in["ctx"].dtype)], 1))   # 77 text + 4 IP tokens
 rb = unet.time_rowbias_table(torch.tensor([981.0]), added, 2 * B)[0].contiguous()
 x = dev_in["lat"].float()
 for _ in range(2):
