@@ -30,7 +30,7 @@ class B200Sampler:
         kv_t, kv_i, n_text, n_ip = kv
         ent = dict(
             x=torch.zeros(sample_shape, device=dev, dtype=torch.float32),
-            rb=torch.zeros(unet_batch, rb_width, device=dev, dtype=torch.float32),
+            rb=torch.zeros(rb_width, device=dev, dtype=torch.float32),       # one row of the blocked rowbias table
             kv_t=torch.empty_like(kv_t), kv_i=None if kv_i is None else torch.empty_like(kv_i),
             graph=None, eps=None)
         self._graphs.clear()          # one resident graph (its private pool holds a full set of activations)
@@ -58,7 +58,7 @@ class B200Sampler:
         unet = self.unet
         dev = unet.device
         kv = unet.context_kv(ctx)
-        table = unet.time_rowbias_table(timesteps, added, unet_batch)      # [steps, unet_batch, sumC]
+        table = unet.time_rowbias_table(timesteps, added, unet_batch)      # [steps, unet_batch * sumC], blocked per ResnetBlock
         n_ip, ip_scale = unet._ip_state()
         key = (kind, tuple(latents.shape), unet_batch, tuple(kv[0].shape), None if kv[1] is None else tuple(kv[1].shape),
                kv[2], kv[3], ip_scale, unet._proc_version, id(unet._packed))

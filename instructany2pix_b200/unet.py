@@ -381,6 +381,7 @@ class B200UNet(nn.Module):
         off = 0
         for n in rn:
             P[n]["temb_slice"] = (off, off + P[n]["wt"].shape[0])
+            P.setdefault("temb_slices", []).append(P[n]["temb_slice"])
             off += P[n]["wt"].shape[0]
         # cross-attention K,V projections of ALL layers as one stacked weight per branch (step-invariant: SURVEY 7.1)
         tb = list(self._iter_tblocks())
@@ -466,7 +467,8 @@ class B200UNet(nn.Module):
         return rb
 
     def time_rowbias_table(self, timesteps, added_cond_kwargs, batch):
-        """``time_rowbias`` for ALL timesteps of a trajectory in five small GEMMs -> fp32 [steps, batch, sum Cout]."""
+        """``time_rowbias`` for ALL timesteps of a trajectory in five small GEMMs -> fp32 [steps, batch * sum Cout] in the BLOCKED
+        layout ``forward_core`` takes as a 1-D ``rowbias`` (block r = the [batch, Cout_r] bias of ResnetBlock r)."""
         P = self.prepare()
         cfg = self.config
         dev = self.device
@@ -483,8 +485,10 @@ class B200UNet(nn.Module):
         a = ops.gemm_smallm(add_in, a1, bias=ab1, act=ops.ACT_SILU)
         aug = ops.gemm_smallm(a, a2, bias=ab2)                              # [batch, ted]
         emb = ops.gemm_smallm(e, w2, bias=b2, residual=aug.repeat(steps, 1))
-        rb = ops.gemm_smallm(emb, P["temb_w"], bias=P["temb_b"], act_in=ops.ACT_SILU)
-        return rb.reshape(steps, batch, -1)
+        rb = ops.gemm_smallm(emb, P["temb_w"], bias=P["temb_b"], act_in=ops.ACT_SILU).reshape(steps, batch, -1)
+        # blocked layout: per step the 17 ResnetBlocks' [batch, Cout] biases one after the other, each block contiguous, so that
+        # the step itself slices views (no copy kernels inside the CUDA graph); one re-layout per request
+        return torch.cat([rb[:, :, lo:hi].reshape(steps, -1) for lo, hi in P["temb_slices"]], dim=1).contiguous()
 
     # ------------------------------------------------------------------ forward
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None,
@@ -538,7 +542,9 @@ class B200UNet(nn.Module):
             else:
                 h = ops.groupnorm(x, skip, p["g1"], p["b1"], G, cfg.norm_eps, True)
             lo, hi = p["temb_slice"]
-            h = ops.conv3x3(h, p["w1"], p["w1"].shape[0], rowbias=rowbias[:, lo:hi].contiguous(), out_dtype=SD, want_colstats=True)
+            # 1-D rowbias = blocked table row (time_rowbias_table): a view; 2-D [batch, sum Cout] (generic forward): a small copy
+            rbias = rowbias[batch * lo:batch * hi].view(batch, hi - lo) if rowbias.ndim == 1 else rowbias[:, lo:hi].contiguous()
+            h = ops.conv3x3(h, p["w1"], p["w1"].shape[0], rowbias=rbias, out_dtype=SD, want_colstats=True)
             h = ops.groupnorm(h, None, p["g2"], p["b2"], G, cfg.norm_eps, True)
             if p["has_sc"]:
                 if raw is not None:
