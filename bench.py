@@ -412,7 +412,7 @@ def main():
                         includes="H2D of the text conditioning + LLM embedding + noise, (prior,) image projector -> IP tokens, 50-step trajectory, VAE decode to fp32 images, D2H of the images",
                         vae_decode_and_readback_ms=ms_decode),
                gpu_launches=int(gpu_launches), roofline=roof)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:                 # contract: rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         t = cpu_unet_step_seconds(L, cores)
         out["cpu_baseline"] = dict(value=1.0 / (50.0 * t), unit="images/sec", cores=cores, kind="port",
