@@ -6,8 +6,8 @@
 // items.  CTA = 6 warps: w0 TMA producer (per item: Q tile + the K / V rows of its head, 2-stage ring; K/V come from L2),
 // w1 tcgen05.mma issuer, w2..w5 softmax + epilogue (one query row per thread):
 //   MMA1: S(TMEM, TK cols fp32) = Q K^T                                     [M128 N=TK K64]   4 instructions
-//   softmax warps: pass 1 row maxima of the two branches, pass 2 p = 2^(s*scale - m) (S is read from TMEM twice, nothing is
-//       kept in registers but the packed P): text p's are packed unnormalised while l_text accumulates, the <= 16 IP p's wait
+//   softmax warps: the whole S row (<= 128 fp32) goes to registers in one round of TMEM loads (S is free for the next MMA1 at
+//       once), then the maxima of the two branches, then p = 2^(s*scale - m): text p's are packed unnormalised while l_text accumulates, the <= 16 IP p's wait
 //       in registers until l_text is known and are packed times scale * l_text / l_ip, so that ONE common 1 / l_text in the
 //       epilogue finishes both branches; P -> TMEM as bf16 pairs (the A operand of MMA2)
 //   MMA2: O(TMEM, 64 cols) = P V                                             [M128 N64 K=TK]   TK / 16 instructions
@@ -131,52 +131,52 @@ xattn_tc_kernel(const __grid_constant__ XaMaps maps, int n_q, int n_text, int n_
       const int qt = w % n_qtiles, bh = w / n_qtiles, h = bh % heads, b = bh / heads;
       mbar_wait(s_full, (uint32_t)(it & 1));
       tc_fence_after();
-      // pass 1: row maxima of the two branches (raw scores; scale > 0)
+      // the whole S row (TK <= 128 columns) goes to registers in ONE round of TMEM loads (all in flight together), which also
+      // frees S for MMA1 of the next item before any math starts; v[] dies pair by pair as the packed P is produced
+      uint32_t v[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);                                    // S may be overwritten by MMA1 of the next item
+      // row maxima of the two branches (raw scores; scale > 0)
       float mt = -INFINITY, mi = -INFINITY;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int j = c * 32 + i;
-          if (j < T1) { if (j < n_text) mt = fmaxf(mt, __uint_as_float(v[i])); }
-          else if (j < TK) { if (j - T1 < n_ip) mi = fmaxf(mi, __uint_as_float(v[i])); }
+          if (j < T1) { if (j < n_text) mt = fmaxf(mt, __uint_as_float(v[c][i])); }
+          else if (j < TK) { if (j - T1 < n_ip) mi = fmaxf(mi, __uint_as_float(v[c][i])); }
         }
       }
       const float nmt = -mt * scale_log2, nmi = (mi == -INFINITY) ? 0.f : -mi * scale_log2;
-      // pass 2: exponentials; text pairs are packed at once, the IP values wait for l_text
+      // exponentials; text pairs are packed at once, the IP values wait for l_text
       uint32_t pk[64];
       float pip[T2 > 0 ? T2 : 1];
       float lt = 0.f, li = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) pk[i] = 0u;
+      for (int i = TK / 2; i < 64; ++i) pk[i] = 0u;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const int j = c * 32 + i;
           if (j < T1) {
-            const float p0 = (j < n_text) ? ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, nmt)) : 0.f;
-            const float p1 = (j + 1 < n_text) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, nmt)) : 0.f;
+            const float p0 = (j < n_text) ? ex2_approx(fmaf(__uint_as_float(v[c][i]), scale_log2, nmt)) : 0.f;
+            const float p1 = (j + 1 < n_text) ? ex2_approx(fmaf(__uint_as_float(v[c][i + 1]), scale_log2, nmt)) : 0.f;
             lt += p0 + p1;
             pk[j >> 1] = pack_bf16x2(p0, p1);
           } else if (j < TK) {
-            const float p0 = (j - T1 < n_ip) ? ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, nmi)) : 0.f;
-            const float p1 = (j + 1 - T1 < n_ip) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, nmi)) : 0.f;
+            const float p0 = (j - T1 < n_ip) ? ex2_approx(fmaf(__uint_as_float(v[c][i]), scale_log2, nmi)) : 0.f;
+            const float p1 = (j + 1 - T1 < n_ip) ? ex2_approx(fmaf(__uint_as_float(v[c][i + 1]), scale_log2, nmi)) : 0.f;
             li += p0 + p1;
             pip[(j - T1) % (T2 > 0 ? T2 : 1)] = p0;
             pip[(j + 1 - T1) % (T2 > 0 ? T2 : 1)] = p1;
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);                                    // S may be overwritten by MMA1 of the next item
       if (T2 > 0) {
         const float f = (li > 0.f) ? ip_scale * lt / li : 0.f;
 #pragma unroll
@@ -201,18 +201,20 @@ xattn_tc_kernel(const __grid_constant__ XaMaps maps, int n_q, int n_text, int n_
       const float inv = 1.f / lt;
       if (elected) bulk_wait_read_all();                                       // the previous item's store has left the staging tile
       named_bar_sync(1, 128);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tO + lane_sel + (uint32_t)(c * 32), v);
+      {
+        uint32_t o[2][32];
+        tmem_ld_32x32(tO + lane_sel, o[0]);
+        tmem_ld_32x32(tO + lane_sel + 32u, o[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          sts128u(sO + (uint32_t)row * 128u + ((uint32_t)((c * 4 + i) ^ (row & 7)) << 4),
-                  pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv),
-                  pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv),
-                  pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv),
-                  pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv));
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128u(sO + (uint32_t)row * 128u + ((uint32_t)((c * 4 + i) ^ (row & 7)) << 4),
+                    pack_bf16x2(__uint_as_float(o[c][8 * i + 0]) * inv, __uint_as_float(o[c][8 * i + 1]) * inv),
+                    pack_bf16x2(__uint_as_float(o[c][8 * i + 2]) * inv, __uint_as_float(o[c][8 * i + 3]) * inv),
+                    pack_bf16x2(__uint_as_float(o[c][8 * i + 4]) * inv, __uint_as_float(o[c][8 * i + 5]) * inv),
+                    pack_bf16x2(__uint_as_float(o[c][8 * i + 6]) * inv, __uint_as_float(o[c][8 * i + 7]) * inv));
       }
       tc_fence_before();
       fence_proxy_async();
