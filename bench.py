@@ -312,6 +312,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")               # keep NCCL's version banner out of stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
 
