@@ -3,7 +3,10 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <mutex>
+
 #include "common.cuh"
+#include "tensormap.cuh"
 
 namespace ia2p {
 
@@ -56,6 +59,34 @@ int sm_count() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || g_sm_count[dev] <= 0) return 148;
   return g_sm_count[dev];
+}
+
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+int make_map_3d_bf16(CUtensorMap* m, const void* base, int64_t cols, int64_t ld, int64_t tokens, int64_t batch, int box_rows,
+                     const char* what) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  IA2P_REQUIRE(enc != nullptr, IA2P_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IA2P_E_ALIGN, "%s: q/k/v/out base not 16-byte aligned", what);
+  const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)tokens, (cuuint64_t)batch};
+  const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)tokens};
+  const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1}, es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IA2P_REQUIRE(r == CUDA_SUCCESS, IA2P_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
 }
 
 }  // namespace ia2p

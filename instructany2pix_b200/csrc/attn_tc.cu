@@ -17,6 +17,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tensormap.cuh"
 
 namespace ia2p {
 
@@ -318,36 +319,6 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn fa_get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(f);
-  });
-  return fn;
-}
-
-static int fa_make_map(CUtensorMap* m, const void* base, int64_t cols, int64_t ld, int64_t n_tokens, int64_t batch) {
-  EncodeTiledFn enc = fa_get_encode();
-  IA2P_REQUIRE(enc != nullptr, IA2P_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
-  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IA2P_E_ALIGN, "flash_self_attn: q/k/v base not 16-byte aligned");
-  const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)n_tokens, (cuuint64_t)batch};
-  const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)n_tokens};
-  const cuuint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  IA2P_REQUIRE(r == CUDA_SUCCESS, IA2P_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-  return 0;
-}
-
 #ifdef IA2P_TC_TRACE
 extern "C" int ia2p_debug_set_fa_trace(void* dev_buffer) {
   unsigned long long* p = static_cast<unsigned long long*>(dev_buffer);
@@ -358,9 +329,9 @@ extern "C" int ia2p_debug_set_fa_trace(void* dev_buffer) {
 int launch_fa_tc(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int64_t batch,
                  int64_t n_tokens, int heads, float softmax_scale, cudaStream_t st) {
   FaMaps maps;
-  if (int e = fa_make_map(&maps.q, q, heads * 64, ld, n_tokens, batch)) return e;
-  if (int e = fa_make_map(&maps.k, k, heads * 64, ld, n_tokens, batch)) return e;
-  if (int e = fa_make_map(&maps.v, v, heads * 64, ld, n_tokens, batch)) return e;
+  if (int e = make_map_3d_bf16(&maps.q, q, heads * 64, ld, n_tokens, batch, 128, "flash_self_attn")) return e;
+  if (int e = make_map_3d_bf16(&maps.k, k, heads * 64, ld, n_tokens, batch, 128, "flash_self_attn")) return e;
+  if (int e = make_map_3d_bf16(&maps.v, v, heads * 64, ld, n_tokens, batch, 128, "flash_self_attn")) return e;
   IA2P_ONCE_PER_DEVICE(
       IA2P_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
       IA2P_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));

@@ -16,6 +16,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tensormap.cuh"
 
 // Two few-row experiments live behind compile-time switches and are NOT part of the shipped library (make variant
 // DEFS="-DIA2P_WITH_SPLITK -DIA2P_WITH_MC"): split-K through an L2 workspace and A-operand TMA multicast in clusters.  Both
@@ -920,30 +921,13 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 }
 
 // ================================================================ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(f);
-  });
-  return fn;
-}
-
 // Tensor map, rank <= 4, dims/strides innermost-first; strides in ELEMENTS (stride of dim 0 is 1).  Default: bf16 operand
 // tiles with SWIZZLE_128B; the epilogue staging slices use fp32 / SWIZZLE_64B and bf16 / SWIZZLE_32B.
 static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
                     const uint32_t* box, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                     CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
   const uint64_t esz = (dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32) ? 4 : 2;
-  EncodeTiledFn enc = get_encode();
+  EncodeTiledFn enc = tensor_map_encoder();
   IA2P_REQUIRE(enc != nullptr, IA2P_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t bx[4], es[4];

@@ -21,6 +21,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tensormap.cuh"
 
 namespace ia2p {
 
@@ -233,37 +234,6 @@ xattn_tc_kernel(const __grid_constant__ XaMaps maps, int n_q, int n_text, int n_
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn xa_get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(f);
-  });
-  return fn;
-}
-
-// 3-D map {heads*64 columns, tokens, batch} over rows of pitch ld elements, box {64, box_rows, 1}
-static int xa_make_map(CUtensorMap* m, const void* base, int64_t cols, int64_t ld, int64_t tokens, int64_t batch, int box_rows) {
-  EncodeTiledFn enc = xa_get_encode();
-  IA2P_REQUIRE(enc != nullptr, IA2P_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
-  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IA2P_E_ALIGN, "cross_attn: q/k/v base not 16-byte aligned");
-  const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)tokens, (cuuint64_t)batch};
-  const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)tokens};
-  const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1}, es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  IA2P_REQUIRE(r == CUDA_SUCCESS, IA2P_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-  return 0;
-}
-
 template <int T1, int T2>
 static int launch_xa(const void* q, int64_t ldq, const void* kt, const void* vt, int64_t ldkv, int n_text, const void* ki,
                      const void* vi, int64_t ldkv_ip, int n_ip, float ip_scale, void* out, int64_t ldo, int64_t batch, int64_t n_q,
@@ -271,15 +241,15 @@ static int launch_xa(const void* q, int64_t ldq, const void* kt, const void* vt,
   constexpr int TK = T1 + T2;
   constexpr int smem = 2 * (kXaQ + 2 * TK * 128) + kXaQ + 1024 + 128;
   XaMaps maps;
-  if (int e = xa_make_map(&maps.q, q, heads * 64, ldq, n_q, batch, 128)) return e;
-  if (int e = xa_make_map(&maps.kt, kt, heads * 64, ldkv, n_text, batch, T1)) return e;
-  if (int e = xa_make_map(&maps.vt, vt, heads * 64, ldkv, n_text, batch, T1)) return e;
-  if (int e = xa_make_map(&maps.o, out, heads * 64, ldo, n_q, batch, 128)) return e;
+  if (int e = make_map_3d_bf16(&maps.q, q, heads * 64, ldq, n_q, batch, 128, "cross_attn")) return e;
+  if (int e = make_map_3d_bf16(&maps.kt, kt, heads * 64, ldkv, n_text, batch, T1, "cross_attn")) return e;
+  if (int e = make_map_3d_bf16(&maps.vt, vt, heads * 64, ldkv, n_text, batch, T1, "cross_attn")) return e;
+  if (int e = make_map_3d_bf16(&maps.o, out, heads * 64, ldo, n_q, batch, 128, "cross_attn")) return e;
   maps.ki = maps.kt;
   maps.vi = maps.vt;
   if (T2 > 0) {
-    if (int e = xa_make_map(&maps.ki, ki, heads * 64, ldkv_ip, n_ip, batch, T2)) return e;
-    if (int e = xa_make_map(&maps.vi, vi, heads * 64, ldkv_ip, n_ip, batch, T2)) return e;
+    if (int e = make_map_3d_bf16(&maps.ki, ki, heads * 64, ldkv_ip, n_ip, batch, T2, "cross_attn")) return e;
+    if (int e = make_map_3d_bf16(&maps.vi, vi, heads * 64, ldkv_ip, n_ip, batch, T2, "cross_attn")) return e;
   }
   IA2P_ONCE_PER_DEVICE(
       IA2P_CUDA(cudaFuncSetAttribute(xattn_tc_kernel<T1, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
