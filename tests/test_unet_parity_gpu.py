@@ -71,7 +71,8 @@ def test_forward_parity_ragged_shapes(B, L):
 
 def test_forward_parity_sdxl_width():
     """the real SDXL-base configuration (2 567 463 684 parameters + 70 IP processors, name-seeded synthetic weights) at a 32x32
-    latent (256^2 image), CFG pair: one teacher-forced forward against the fp32 CPU oracle.  ~2 min (weight synthesis dominates)."""
+    latent (256^2 image) AND at the full 128x128 latent (1024^2 image), CFG pair: teacher-forced forwards against the fp32 CPU
+    oracle.  ~1 min (weight synthesis dominates)."""
     from oracle.attention import IPAttnProcessor2_0
     from oracle.synth import synth_input, synth_state_dict
     from oracle.unet import SDXL_BASE, OracleUNet
@@ -97,6 +98,15 @@ def test_forward_parity_sdxl_width():
     out = b(cu(x), 601, cu(ctx), added_cond_kwargs=cu(added))[0]
     e = rel(out.cpu(), ref)
     print(f"SDXL-width forward (2.57 B parameters): eps rel-L2 = {e:.2e}")
+    assert e < EPS_TOL
+    # the same models at BASELINE.json's FULL size: 128x128 latent (1024^2 image), CFG pair -- every kernel at the shapes the
+    # benchmark runs (16 384 / 4 096 / 1 024 tokens per image), ~10 s of CPU oracle on the GPU box's host cores
+    x = synth_input("full/x128", (2, 4, 128, 128))
+    added = dict(text_embeds=synth_input("full/pooled", (2, 1280)), time_ids=torch.tensor([[1024.0, 1024.0, 0.0, 0.0, 1024.0, 1024.0]] * 2))
+    ref = o(x, torch.tensor(981), ctx, added_cond_kwargs=added)[0]
+    out = b(cu(x), 981, cu(ctx), added_cond_kwargs=cu(added))[0]
+    e = rel(out.cpu(), ref)
+    print(f"SDXL-width forward at the full 1024^2 size: eps rel-L2 = {e:.2e}")
     assert e < EPS_TOL
 
 
