@@ -108,6 +108,19 @@ def test_forward_parity_sdxl_width():
     e = rel(out.cpu(), ref)
     print(f"SDXL-width forward at the full 1024^2 size: eps rel-L2 = {e:.2e}")
     assert e < EPS_TOL
+    # north-star image gate at the full size: a free-running 3-step DDIM + CFG trajectory (guidance 10) on both paths from the same
+    # start noise, both final latents through the SAME decoder (the fp32 oracle VAE at SDXL width): PSNR >= 35 dB
+    from oracle.vae import SDXL_VAE, OracleVAEDecoder, psnr
+    lat = synth_input("full/lat128", (1, 4, 128, 128))
+    ref_lat = osampler.generate(o, lat, ctx, added, num_inference_steps=3, guidance_scale=10.0)
+    out_lat = B200Sampler(b).generate(cu(lat), cu(ctx), cu(added), num_inference_steps=3, guidance_scale=10.0).cpu()
+    e = rel(out_lat, ref_lat)
+    dec = OracleVAEDecoder(SDXL_VAE).eval()
+    dec.load_state_dict(synth_state_dict(dec, 11))
+    img_ref, img_out = dec.decode(ref_lat), dec.decode(out_lat)
+    db = psnr(img_out, img_ref, data_range=float(img_ref.max() - img_ref.min()))
+    print(f"full-size 3-step trajectory: final latent rel-L2 = {e:.2e}, decoded 1024^2 image PSNR = {db:.1f} dB (gate 35)")
+    assert e < 5e-2 and db >= 35.0
 
 
 def test_forward_parity_refiner_topology():

@@ -38,8 +38,11 @@ def build(cfg):
     return dec, enc, vae
 
 
-@pytest.mark.parametrize("cfg,L,B", [(SMALL, 16, 2), (SMALL, 24, 1), (SDXL_VAE, 32, 1)], ids=["small-16", "small-24", "sdxl-width-32"])
+@pytest.mark.parametrize("cfg,L,B", [(SMALL, 16, 2), (SMALL, 24, 1), (SDXL_VAE, 32, 1), (SDXL_VAE, 128, 1)],
+                         ids=["small-16", "small-24", "sdxl-width-32", "sdxl-width-128-full-1024px"])
 def test_decode_parity(cfg, L, B):
+    """the last case is BASELINE.json's full size: a 128x128 latent decoded to 1024^2 at the real SDXL VAE width (16 384-token
+    single-head mid attention, 10.5 TFLOP); the fp32 CPU oracle takes some tens of seconds there"""
     dec, _, vae = build(cfg)
     lat = synth_input("vae/lat", (B, 4, L, L), seed=L) * 0.9            # sampler-scale latents (std ~ 0.9)
     ref = dec.decode(lat)
