@@ -20,12 +20,14 @@ class B200Sampler:
         self.unet = unet
         self.scheduler = scheduler or B200DDIMScheduler()
         self.use_cuda_graph = use_cuda_graph
+        self.max_graphs = 2
         self._graphs = {}
 
     # ------------------------------------------------------------------ CUDA-graph plumbing
     def _static(self, key, sample_shape, unet_batch, kv, rb_width, dev):
         ent = self._graphs.get(key)
         if ent is not None:
+            self._graphs[key] = self._graphs.pop(key)      # most recently used last
             return ent
         kv_t, kv_i, n_text, n_ip = kv
         ent = dict(
@@ -33,7 +35,10 @@ class B200Sampler:
             rb=torch.zeros(rb_width, device=dev, dtype=torch.float32),       # one row of the blocked rowbias table
             kv_t=torch.empty_like(kv_t), kv_i=None if kv_i is None else torch.empty_like(kv_i),
             graph=None, eps=None)
-        self._graphs.clear()          # one resident graph (its private pool holds a full set of activations)
+        # small LRU: an edit request alternates the inversion graph (batch B) and the CFG graph (batch 2B); each resident graph's
+        # private pool holds a full set of activations, so older shapes are dropped (B200HotPath.edit never recaptures in steady state)
+        while len(self._graphs) >= self.max_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
         self._graphs[key] = ent
         return ent
 
@@ -74,10 +79,18 @@ class B200Sampler:
         """``polar_intrtpolate(latent_inv, randn_like(latent_inv), alpha)`` (pipeline.py:295-300, :332-336): the inverted
         latent is blended with fresh noise and the blend is rescaled to the blended norm.  ``noise`` may be supplied (parity
         tests); otherwise it is drawn like the reference does (global RNG or ``generator``)."""
-        x = latent_inv.to(self.unet.device, torch.float32)
+        x = latent_inv.to(self.unet.device, torch.float32).contiguous()
         if noise is None:
             noise = torch.randn(x.shape, device=x.device, dtype=torch.float32, generator=generator)
-        return ops.polar_interpolate(x, noise.to(x.device, torch.float32), alpha)
+        noise = noise.to(x.device, torch.float32).contiguous()
+        if x.shape[0] == 1:
+            return ops.polar_interpolate(x, noise, alpha)
+        # the reference takes the norms over the whole tensor and only ever runs one image (pipeline.py:295-300, :332-336); a batch
+        # here is a batch of independent requests, so every sample is blended with ITS OWN norms
+        out = torch.empty_like(x)
+        for b in range(x.shape[0]):
+            ops.polar_interpolate(x[b], noise[b], alpha, out=out[b])
+        return out
 
     # ------------------------------------------------------------------ generation (CFG, DDIM eta=0)
     @torch.no_grad()
@@ -91,6 +104,8 @@ class B200Sampler:
         ``strength`` < 1 -> only the last int(N * strength) steps run, starting from ``add_noise(init_latents, latents, t_start)``.
         Inpainting (gdino/lib.py:85-102, [3P] StableDiffusionXLInpaintPipeline with a 4-channel UNet): additionally
         ``inpaint_mask`` (B,1,L,L), 1 = repaint: after every step the kept region is reset to the re-noised original."""
+        if inpaint_mask is not None and init_latents is None:
+            raise ValueError("generate(inpaint_mask=...) needs init_latents (the encoded original the kept region is reset to)")
         s = self.scheduler
         s.set_timesteps(num_inference_steps)
         B = latents.shape[0]

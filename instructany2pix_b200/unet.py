@@ -413,13 +413,17 @@ class B200UNet(nn.Module):
         return 0, 0.0
 
     def context_kv(self, ctx):
-        """K,V of every cross-attention layer for this context: [B*n_text, sum 2C], [B*n_ip, sum 2C] (cached)."""
+        """K,V of every cross-attention layer for this context: [B*n_text, sum 2C], [B*n_ip, sum 2C].
+
+        One entry is cached for the drop-in ``forward()`` path (the reference passes the SAME ``prompt_embeds`` tensor object on
+        every step of a loop, custom_pipelines.py:338-345).  The entry holds a reference to that tensor and hits only on object
+        identity + unchanged version counter: an address can never be recycled to a different request while it is cached."""
         P = self.prepare()
         n_ip, _ = self._ip_state()
-        key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), self._proc_version, n_ip)
-        hit = self._kv_cache.get(key)
-        if hit is not None:
-            return hit
+        hit = self._kv_cache.get("entry")
+        if (hit is not None and hit["ctx"] is ctx and hit["version"] == ctx._version and hit["proc"] == self._proc_version
+                and hit["n_ip"] == n_ip):
+            return hit["val"]
         self._kv_cache.clear()
         B, S, D = ctx.shape
         n_text = S - n_ip                                    # attention_processor.py:350-354 (also the 77-token quirk)
@@ -431,7 +435,7 @@ class B200UNet(nn.Module):
             ip = c[:, n_text:].reshape(B * n_ip, D).contiguous()
             kv_i = ops.gemm(ip, P["wkv_ip"])
         val = (kv_t, kv_i, n_text, n_ip)
-        self._kv_cache[key] = val
+        self._kv_cache["entry"] = dict(ctx=ctx, version=ctx._version, proc=self._proc_version, n_ip=n_ip, val=val)
         return val
 
     def time_rowbias(self, timestep, added_cond_kwargs, batch):
@@ -443,8 +447,14 @@ class B200UNet(nn.Module):
         te, tid = added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"]
         key = None
         if not (torch.is_tensor(timestep) and timestep.is_cuda):
-            key = (float(timestep), te.data_ptr(), te._version, tid.data_ptr(), tid._version, batch)
-            hit = self._temb_cache.get(key)
+            # per-timestep cache for the drop-in loop, valid only for the SAME conditioning tensor objects (held here, so their
+            # addresses cannot be recycled) at unchanged version counters
+            c = self._temb_cache
+            if not (c.get("te") is te and c.get("tid") is tid and c.get("ver") == (te._version, tid._version)):
+                c.clear()
+                c.update(te=te, tid=tid, ver=(te._version, tid._version), rows={})
+            key = (float(timestep), batch)
+            hit = c["rows"].get(key)
             if hit is not None:
                 return hit
             t = torch.full((batch,), float(timestep), device=dev, dtype=torch.float32)
@@ -461,9 +471,10 @@ class B200UNet(nn.Module):
         emb = ops.gemm_smallm(a, a2, bias=ab2, residual=emb)
         rb = ops.gemm_smallm(emb, P["temb_w"], bias=P["temb_b"], act_in=ops.ACT_SILU)
         if key is not None:
-            if len(self._temb_cache) > 256:
-                self._temb_cache.clear()
-            self._temb_cache[key] = rb
+            rows = self._temb_cache["rows"]
+            if len(rows) > 256:
+                rows.clear()
+            rows[key] = rb
         return rb
 
     def time_rowbias_table(self, timesteps, added_cond_kwargs, batch):

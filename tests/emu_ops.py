@@ -48,6 +48,26 @@ def axpby(eps, x, c_x, c_e, out=None):
     return v
 
 
+def polar_interpolate(x, y, alpha, out=None):
+    """pipeline.py:295-300 over the WHOLE tensor it is given"""
+    x, y = x.float(), y.float()
+    ll = x * alpha + y * (1 - alpha)
+    v = ll / ll.norm() * (x.norm() * alpha + y.norm() * (1 - alpha))
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
+def inpaint_blend(latents, orig, noise, mask, c_x, c_e, out=None):
+    ref = c_x * orig + (c_e * noise if noise is not None else 0.0)
+    v = (1 - mask) * ref + mask * latents
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
 def prior_cfg_ddpm_step(x0_pair, x, noise, sqrt_a, sqrt_1ma, g, c_x0, c_x, sigma, out=None):
     x0_pair = x0_pair.reshape(2, -1)
     xf = x.reshape(-1)

@@ -103,3 +103,70 @@ def test_sampler_generate_and_invert(emu):
     ref_i = osampler.invert(o, lat, c1, add1, num_inference_steps=3)
     out_i = s.invert(lat, c1, add1, num_inference_steps=3)
     assert rel(out_i, ref_i) < 1.5e-2
+
+
+def test_kv_and_temb_caches_never_serve_a_recycled_address(emu):
+    """the K/V and time-embedding caches were keyed on data_ptr()/_version; a freed context's address is handed to
+    the next request's tensor (same shape, version 0) -> stale conditioning.  Now the entry holds the tensor and hits on identity."""
+    o, b = build_pair(True)
+    lat, ctx, added = make_inputs(TINY)
+    seen = set()
+    prev_k = None
+    stale = 0
+    for i in range(10):
+        c = torch.randn(2, 81, TINY.cross_attention_dim)            # a fresh request: same shape, new contents
+        seen.add(c.data_ptr())
+        k = b.context_kv(c)[0].clone()
+        assert b.context_kv(c)[0] is b._kv_cache["entry"]["val"][0]  # same object again -> hit
+        if prev_k is not None and torch.equal(k, prev_k):
+            stale += 1
+        prev_k = k
+        del c
+    assert stale == 0
+    # in-place modification of the SAME tensor bumps the version counter -> recomputed
+    c = torch.randn(2, 81, TINY.cross_attention_dim)
+    k0 = b.context_kv(c)[0].clone()
+    c.mul_(2.0)
+    assert not torch.equal(b.context_kv(c)[0], k0)
+    # time-embedding bias: fresh pooled embeddings at a (possibly recycled) address must not hit the previous prompt's rows
+    prev = None
+    for i in range(10):
+        a = dict(text_embeds=torch.randn_like(added["text_embeds"]), time_ids=added["time_ids"].clone())
+        rb = b.time_rowbias(981, a, 2).clone()
+        assert b.time_rowbias(981, a, 2) is b._temb_cache["rows"][(981.0, 2)]
+        assert prev is None or not torch.equal(rb, prev)
+        prev = rb
+        del a
+
+
+def test_sampler_keeps_inversion_and_cfg_graph_entries(emu):
+    """`_static` cleared every entry on a new key, so an edit request (invert -> generate) recaptured both graphs."""
+    o, b = build_pair(True)
+    lat, ctx, added = make_inputs(TINY, B=1, L=8)
+    s = B200Sampler(b, use_cuda_graph=False)
+    c1, add1 = ctx[1:, :77], {k: v[1:] for k, v in added.items()}
+    s.invert(lat, c1, add1, num_inference_steps=2)
+    s.generate(lat, ctx, added, num_inference_steps=2)
+    ents = {k[0]: id(v) for k, v in s._graphs.items()}
+    assert set(ents) == {"inv", "gen"}
+    s.invert(lat, c1, add1, num_inference_steps=2)
+    s.generate(lat, ctx, added, num_inference_steps=2)
+    assert {k[0]: id(v) for k, v in s._graphs.items()} == ents
+
+
+def test_inpaint_mask_needs_init_latents(emu):
+    import pytest
+    o, b = build_pair(True)
+    lat, ctx, added = make_inputs(TINY, B=1, L=8)
+    with pytest.raises(ValueError, match="init_latents"):
+        B200Sampler(b, use_cuda_graph=False).generate(lat, ctx, added, num_inference_steps=2, inpaint_mask=torch.ones(1, 1, 8, 8))
+
+
+def test_start_latent_is_per_sample(emu):
+    """a batch is a batch of independent requests: sample b of a batched call == the single-sample call (reference: B = 1 only)"""
+    o, b = build_pair(True)
+    s = B200Sampler(b, use_cuda_graph=False)
+    x, n = torch.randn(3, 4, 8, 8), torch.randn(3, 4, 8, 8) * 2.0
+    out = s.start_latent(x, 0.7, noise=n)
+    for i in range(3):
+        assert torch.allclose(out[i:i + 1], s.start_latent(x[i:i + 1], 0.7, noise=n[i:i + 1]), atol=1e-6)

@@ -1,8 +1,16 @@
-// Stand-alone experiment: how long does one tcgen05.mma.kind::f16 take as a function of its N (and of where A lives)?
+// Stand-alone experiment: how long does one tcgen05.mma.kind::f16 take as a function of its N, of where A lives, of the CTA group
+// and of the accumulator dependency chain?
 // One CTA per SM, one thread issues `iters` groups of 4 MMAs (one 64-wide k-block: +32 B descriptor steps, like the GEMM main
 // loop) on whatever bytes are in shared memory, then commits and waits; clock64 around the whole chain.
-//   mode 0: A and B from shared memory (SWIZZLE_128B K-major)        -- tc_gemm_kernel
-//   mode 1: A from TMEM, B from shared memory (MN-major)             -- the P.V MMA of fa_tc_kernel
+//   mode 0: A and B from shared memory (SWIZZLE_128B K-major), one accumulator       -- tc_gemm_kernel<*, 1, *>
+//   mode 1: A from TMEM, B from shared memory (MN-major)                            -- the P.V MMA of fa_tc_kernel
+//   mode 2/4: round-robin over 2/4 accumulators with the B rows split likewise (round 1)
+//   mode 10: like 0, but consecutive MMAs alternate between TWO accumulators (same operands): is the per-instruction overhead a
+//            read-after-write bubble on the accumulator?
+//   mode 11: like 0, with a tcgen05.commit after every 4 MMAs (the main loop's stage release)
+//   mode 20: cta_group::2, M = 256 over a CTA pair (each CTA: its 128 A rows + N/2 B rows), one accumulator -- tc_gemm_kernel<*, 2, *>
+//   mode 21: cta_group::2, alternating between two accumulators
+//   mode 22: cta_group::2, commit (multicast to both CTAs) after every 4 MMAs
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I instructany2pix_b200/csrc -o tools/mmabench tools/mmabench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -13,10 +21,10 @@ using namespace ia2p;
 __global__ void __launch_bounds__(128, 1) mma_chain(int n, int mode, int iters, int ctas_active, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, slot = bar + 8;
+  const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, slot = bar + 16, bar2 = bar + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= ctas_active) return;
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
   if (warp == 0) { tmem_alloc(slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -29,12 +37,14 @@ __global__ void __launch_bounds__(128, 1) mma_chain(int n, int mode, int iters, 
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (mode == 0) umma_bf16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
-        else if (mode >= 2) {                 // mode = number of independent accumulators, round-robin (B rows split likewise)
+        if (mode == 0 || mode == 11) umma_bf16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+        else if (mode == 10) umma_bf16(tmem + (uint32_t)((k & 1) * 256), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+        else if (mode == 2 || mode == 4) {    // mode = number of independent accumulators, round-robin (B rows split likewise)
           for (int a = 0; a < mode; ++a)
             umma_bf16(tmem + (uint32_t)(a * n), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k) + (uint64_t)((a * n * 128) >> 4), idesc, 1u);
         } else umma_bf16_ts(tmem, tmem + 256u + (uint32_t)(k * 8), umma_desc_sw128_mn(sB + k * 2048, 16384), idesc, 1u);
       }
+      if (mode == 11) umma_commit(bar2);
     }
     umma_commit(bar);
     mbar_wait(bar, 0);
@@ -45,17 +55,56 @@ __global__ void __launch_bounds__(128, 1) mma_chain(int n, int mode, int iters, 
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// CTA pair: cluster of 2, the leader issues tcgen05.mma.cta_group::2 (M = 256, each CTA's TMEM receives its 128 rows)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_chain_pair(int n, int mode, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, slot = bar + 16, bar2 = bar + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc_2sm(slot, 512); tmem_relinquish_2sm(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+  if (warp == 1 && lane == 0) {
+    const long long t0 = clock64();
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, n, 0);
+      const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sB);
+      for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t d = (mode == 21) ? tmem + (uint32_t)((k & 1) * 256) : tmem;
+          umma_bf16_2sm(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+        }
+        if (mode == 22) umma_commit_2sm_mc(bar2, 3);
+      }
+      umma_commit_2sm_mc(bar, 3);
+    }
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc_2sm(tmem, 512); }
+}
+
 int main() {
   long long* d;
   cudaMalloc(&d, 148 * sizeof(long long));
   const int smem = 16384 + 32768 + 1024 + 64;
   cudaFuncSetAttribute(mma_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(mma_chain_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 2000;
-  for (int mode : {0, 1, 2, 4})
+  for (int mode : {0, 1, 2, 4, 10, 11})
     for (int ctas : {148})
       for (int n : {16, 32, 64, 96, 128, 160, 192, 256}) {
         if (mode == 1 && n > 128) continue;                 // MN-major B of 64-element atoms: keep to what the kernel uses
-        if (mode >= 2 && (mode * n > 512 || n % 64 != 0 || mode * n * 128 > 32768)) continue;
+        if ((mode == 2 || mode == 4) && (mode * n > 512 || n % 64 != 0 || mode * n * 128 > 32768)) continue;
+        if (mode >= 10 && n < 64) continue;
         for (int rep = 0; rep < 2; ++rep) mma_chain<<<148, 128, smem>>>(n, mode, iters, ctas, d);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("mode %d n %d: %s\n", mode, n, cudaGetErrorString(e)); return 1; }
@@ -63,9 +112,23 @@ int main() {
         cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
         double s = 0;
         for (int i = 0; i < ctas; ++i) s += (double)h[i];
-        const double clk = s / ctas / (iters * 4.0 * (mode >= 2 ? mode : 1));
-        printf("mode %d (%s) CTAs %3d  M128 N%-3d K16: %6.1f clk per MMA  -> %6.0f MAC/clk/SM (peak 4096)\n", mode,
-               mode == 0 ? "A smem" : mode == 1 ? "A tmem" : "A smem, round-robin accumulators", ctas, n, clk, 128.0 * n * 16 / clk);
+        const double clk = s / ctas / (iters * 4.0 * ((mode == 2 || mode == 4) ? mode : 1));
+        printf("mode %2d (%s) CTAs %3d  M128 N%-3d K16: %6.1f clk per MMA  -> %6.0f MAC/clk/SM (peak 4096)\n", mode,
+               mode == 0 ? "A smem" : mode == 1 ? "A tmem" : mode == 10 ? "A smem, 2 alternating accumulators" :
+               mode == 11 ? "A smem, commit per 4" : "A smem, round-robin accumulators", ctas, n, clk, 128.0 * n * 16 / clk);
       }
+  for (int mode : {20, 21, 22})
+    for (int n : {64, 128, 160, 192, 256}) {
+      for (int rep = 0; rep < 2; ++rep) mma_chain_pair<<<148, 128, smem>>>(n, mode, iters, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mode %d n %d: %s\n", mode, n, cudaGetErrorString(e)); return 1; }
+      long long h[148];
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      double s = 0;
+      for (int i = 0; i < 148; i += 2) s += (double)h[i];   // leader CTAs
+      const double clk = s / 74 / (iters * 4.0);
+      printf("mode %2d (cta_group::2%s) pairs 74  M256 N%-3d K16: %6.1f clk per MMA  -> %6.0f MAC/clk/SM (peak 4096)\n", mode,
+             mode == 21 ? ", 2 alternating accumulators" : mode == 22 ? ", commit per 4" : "", n, clk, 128.0 * n * 16 / clk);
+    }
   return 0;
 }
