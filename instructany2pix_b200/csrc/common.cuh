@@ -65,6 +65,18 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // ---------------------------------------------------------------- small device utilities
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// Warp index as a value the compiler KNOWS is warp-uniform (a shuffle from lane 0): role branches on it are uniform branches, so
+// everything computed inside them from uniform inputs can live in uniform registers.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// One lane of a converged warp (elect.sync).  Unlike `lane == 0`, ptxas treats the guarded region as single-lane code with uniform
+// operands: tcgen05.mma / tcgen05.commit / TMA issue compile to ONE instruction with uniform-register operands instead of a
+// per-lane "waterfall" loop (ELECT + 7 x R2UR.BROADCAST + branch around every UTCHMMA -- measured ~150 clk of issue per MMA,
+// which made the single issuing thread, not the tensor pipe, the bottleneck of the GEMM main loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 // Exact (erf) GELU, v * Phi(v), with Phi(-|v|) = 0.5 erfc(|v| / sqrt 2) from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 in
@@ -160,8 +172,13 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 #define TRACE_DECL(name) long long name = 0
 #define TRACE_T0(v) const long long v = clock64()
 #define TRACE_ADD(acc, v) acc += clock64() - v
+// IA2P_TRACE_ROW: row of this CTA in the trace buffer (default: blockIdx.x, i.e. the buffer describes the LAST launch; a kernel may
+// define it as launch_id * stride + blockIdx.x to keep one row per (launch, CTA) of a whole CUDA-graph step)
+#ifndef IA2P_TRACE_ROW
+#define IA2P_TRACE_ROW ((size_t)blockIdx.x)
+#endif
 #define TRACE_PUT_AT(cta, slot, val) do { if (IA2P_TRACE_BUF != nullptr && lane == 0) IA2P_TRACE_BUF[(size_t)(cta) * 16 + (slot)] = (unsigned long long)(val); } while (0)
-#define TRACE_PUT(slot, val) TRACE_PUT_AT(blockIdx.x, slot, val)
+#define TRACE_PUT(slot, val) TRACE_PUT_AT(IA2P_TRACE_ROW, slot, val)
 #else
 #define TRACE_DECL(name)
 #define TRACE_T0(v)

@@ -15,6 +15,9 @@
 #include <cstdlib>
 #include <mutex>
 
+#ifdef IA2P_TC_TRACE
+#define IA2P_TRACE_ROW ((size_t)p.trace_id * (size_t)g_tc_trace_stride + (size_t)blockIdx.x)
+#endif
 #include "common.cuh"
 #include "tensormap.cuh"
 
@@ -92,6 +95,7 @@ struct TcParams {
 #ifdef IA2P_TC_TRACE
 #define IA2P_TRACE_BUF g_tc_trace
 __device__ unsigned long long* g_tc_trace = nullptr;
+__device__ int g_tc_trace_stride = 0;                          // 0: one row per CTA (last launch); > 0: rows per launch (whole-step traces)
 __device__ unsigned long long* g_tc_timeline = nullptr;
 static int g_tc_launch_id = 0;                                 // host: id handed to the next launch (fixed per graph node)
 #endif
@@ -240,7 +244,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
 #ifdef IA2P_WITH_MC
   const uint32_t mc = (CG == 1 && p.mc > 1) ? (uint32_t)p.mc : 1u;      // A-multicast cluster size
@@ -333,7 +337,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           TRACE_T0(tw0);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           TRACE_ADD(tr_wait_empty, tw0);
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
             if (CG == 2) {
               // Both CTAs' loads complete on the LEADER's full barrier (peer-bit-masked address).  Only the leader arrives
@@ -363,7 +367,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
       if (!pf_done) {                                   // first tile's loads issued: now pull this CTA's slice of the next weights
         pf_done = true;
-        if (lane == 0) {
+        if (elect_one()) {
           const long long per = ((p.pf_bytes / (long long)gridDim.x + 4095) / 4096) * 4096;
           const long long lo = per * (long long)blockIdx.x;
           long long hi = lo + per;
@@ -401,8 +405,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         TRACE_T0(tf0);
         mbar_wait(full_bar(stage), phase);
         TRACE_ADD(tr_wait_full, tf0);
+#ifdef IA2P_TC_TRACE
+        if (it == 0 && kb == 0) TRACE_PUT(10, clock64() - tf0);        // cold start: TMA issue -> first operands landed
+#endif
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
@@ -425,6 +432,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
     }
     TRACE_ADD(tr_loop, tl0);
+#ifdef IA2P_TC_TRACE
+    TRACE_PUT(15, gtime_ns());                                        // all MMAs issued
+#endif
     TRACE_PUT(2, tr_wait_full);
     TRACE_PUT(3, tr_wait_tempty);
     TRACE_PUT(4, tr_loop);
@@ -656,6 +666,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     if (elected) bulk_wait_read_all();                          // staging memory must outlive the last store's read
     if (warp == 2) { TRACE_PUT(6, tr_wait_tfull); TRACE_PUT(7, tr_busy); }
+#ifdef IA2P_TC_TRACE
+    if (warp == 2) TRACE_PUT(11, gtime_ns());                          // this CTA's epilogue is done
+#endif
   } else {
     // ------------------------------------------------------------ epilogue (4 warps, one accumulator row per thread)
     // TMEM -> registers hands every thread one output row.  Shared memory is NOT used here on purpose: with
@@ -902,6 +915,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       TRACE_ADD(tr_busy, tb0);
     }
     if (warp == 2) { TRACE_PUT(6, tr_wait_tfull); TRACE_PUT(7, tr_busy); }
+#ifdef IA2P_TC_TRACE
+    if (warp == 2) TRACE_PUT(11, gtime_ns());                          // this CTA's epilogue is done
+#endif
   }
 
   // ------------------------------------------------------------ teardown
@@ -1222,6 +1238,9 @@ extern "C" int ia2p_debug_next_launch_id(void) { return g_tc_launch_id; }
 extern "C" int ia2p_debug_set_trace(void* dev_buffer) {       // debug build only; not part of include/ia2p.h
   unsigned long long* p = static_cast<unsigned long long*>(dev_buffer);
   return (int)cudaMemcpyToSymbol(g_tc_trace, &p, sizeof(p));
+}
+extern "C" int ia2p_debug_set_trace_stride(int rows_per_launch) {   // > 0: trace row = launch id * rows_per_launch + blockIdx.x
+  return (int)cudaMemcpyToSymbol(g_tc_trace_stride, &rows_per_launch, sizeof(int));
 }
 #endif
 

@@ -11,6 +11,9 @@
 //   mode 20: cta_group::2, M = 256 over a CTA pair (each CTA: its 128 A rows + N/2 B rows), one accumulator -- tc_gemm_kernel<*, 2, *>
 //   mode 21: cta_group::2, alternating between two accumulators
 //   mode 22: cta_group::2, commit (multicast to both CTAs) after every 4 MMAs
+//   mode 23: like 22, plus the main loop's per-k-block mbarrier wait (on a barrier whose phase completed long ago) + tcgen05 fence
+//            BEFORE the 4 MMAs: does the issuing thread run far enough ahead of the tensor pipe to hide that latency?
+//   mode 24: like 23, but the wait for the NEXT k-block sits between the 2nd and 3rd MMA of the current one (software pipelining)
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I instructany2pix_b200/csrc -o tools/mmabench tools/mmabench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -59,10 +62,10 @@ __global__ void __launch_bounds__(128, 1) mma_chain(int n, int mode, int iters, 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_chain_pair(int n, int mode, int iters, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, slot = bar + 16, bar2 = bar + 8;
+  const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, slot = bar + 32, bar2 = bar + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); mbar_init(bar + 24, 1); fence_barrier_init(); mbar_arrive(bar + 24); }
   if (warp == 0) { tmem_alloc_2sm(slot, 512); tmem_relinquish_2sm(); }
   tc_fence_before();
   cluster_sync_all();
@@ -73,19 +76,82 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_chain_pa
     if (rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(256, n, 0);
       const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sB);
+      const uint32_t bar3 = bar + 24;                     // completes phase 0 once, then stays "already complete" for parity 0
       for (int i = 0; i < iters; ++i) {
+        if (mode == 23) { mbar_wait(bar3, 0); tc_fence_after(); }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t d = (mode == 21) ? tmem + (uint32_t)((k & 1) * 256) : tmem;
           umma_bf16_2sm(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+          if (mode == 24 && k == 1) { mbar_wait(bar3, 0); tc_fence_after(); }
         }
-        if (mode == 22) umma_commit_2sm_mc(bar2, 3);
+        if (mode >= 22) umma_commit_2sm_mc(bar2, 3);
       }
       umma_commit_2sm_mc(bar, 3);
     }
     mbar_wait(bar, 0);
     const long long t1 = clock64();
     out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc_2sm(tmem, 512); }
+}
+
+
+// The GEMM main loop minus TMA and epilogue: the leader walks a 6-stage ring of REAL (random bf16) operands, with the per-k-block
+// wait + fence + 4 MMAs + commit sequence; optional spinning warps like the kernel's idle epilogue / producer warps.
+//   mode 30: zeros in smem, one stage;  31: random data, one stage;  32: random data, 6-stage ring;  33: 32 + 8 warps spinning on
+//   mbarrier.try_wait (the epilogue warps waiting for an accumulator);  34: 33 with the spin replaced by one long suspended wait
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) mma_ring_pair(int mode, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar = base + 6 * 32768, bar2 = bar + 8, bar3 = bar + 24, slot = bar + 32, barN = bar + 40;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  // fill the ring
+  uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)));
+  for (int i = threadIdx.x; i < 6 * 32768 / 4; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 97u;
+    h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+    // two bf16 in [-1, 1): exponent 0x3f (0.5..1) / random sign, random mantissa
+    const uint32_t v = (mode == 30) ? 0u : ((h & 0x807f807fu) | 0x3f003f00u);
+    sm[i] = v;
+  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); mbar_init(bar3, 1); mbar_init(barN, 1); fence_barrier_init(); mbar_arrive(bar3); }
+  if (warp == 0) { tmem_alloc_2sm(slot, 512); tmem_relinquish_2sm(); }
+  fence_proxy_async();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+  if (warp == 1 && lane == 0) {
+    const long long t0 = clock64();
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, 256, 0);
+      int stage = 0;
+      for (int i = 0; i < iters; ++i) {
+        mbar_wait(bar3, 0); tc_fence_after();
+        const uint32_t a = base + (mode >= 32 ? stage * 32768 : 0);
+        const uint64_t da = umma_desc_sw128(a), db = umma_desc_sw128(a + 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_2sm(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+        umma_commit_2sm_mc(bar2, 3);
+        if (++stage == 6) stage = 0;
+      }
+      umma_commit_2sm_mc(bar, 3);
+    }
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+    mbar_arrive(barN);                                     // release the spinning warps
+  } else if (warp >= 2 && mode >= 33) {
+    if (mode == 33) { while (!mbar_try_wait(barN, 0)) { if (clock64() < 0) __trap(); } }
+    else {
+      uint32_t ok = 0;
+      while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                               : "=r"(ok) : "r"(barN), "r"(0u), "r"(0x989680u) : "memory");
+    }
   }
   tc_fence_before();
   cluster_sync_all();
@@ -117,7 +183,7 @@ int main() {
                mode == 0 ? "A smem" : mode == 1 ? "A tmem" : mode == 10 ? "A smem, 2 alternating accumulators" :
                mode == 11 ? "A smem, commit per 4" : "A smem, round-robin accumulators", ctas, n, clk, 128.0 * n * 16 / clk);
       }
-  for (int mode : {20, 21, 22})
+  for (int mode : {20, 22, 23, 24})
     for (int n : {64, 128, 160, 192, 256}) {
       for (int rep = 0; rep < 2; ++rep) mma_chain_pair<<<148, 128, smem>>>(n, mode, iters, d);
       cudaError_t e = cudaDeviceSynchronize();
@@ -128,7 +194,23 @@ int main() {
       for (int i = 0; i < 148; i += 2) s += (double)h[i];   // leader CTAs
       const double clk = s / 74 / (iters * 4.0);
       printf("mode %2d (cta_group::2%s) pairs 74  M256 N%-3d K16: %6.1f clk per MMA  -> %6.0f MAC/clk/SM (peak 4096)\n", mode,
-             mode == 21 ? ", 2 alternating accumulators" : mode == 22 ? ", commit per 4" : "", n, clk, 128.0 * n * 16 / clk);
+             mode == 21 ? ", 2 alternating accumulators" : mode == 22 ? ", commit per 4" : mode == 23 ? ", wait+fence then 4 MMAs, commit" : mode == 24 ? ", wait+fence between MMA 2 and 3, commit" : "", n, clk, 128.0 * n * 16 / clk);
     }
+  {
+    const int smem2 = 6 * 32768 + 1024 + 128;
+    cudaFuncSetAttribute(mma_ring_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    for (int mode : {30, 31, 32, 33, 34}) {
+      for (int rep = 0; rep < 2; ++rep) mma_ring_pair<<<148, 320, smem2>>>(mode, 4000, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("ring mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
+      long long h[148];
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      double s = 0;
+      for (int i = 0; i < 148; i += 2) s += (double)h[i];
+      printf("ring mode %d (%s): %6.1f clk per k-block of 4 MMAs (M256 N256; ideal 512)\n", mode,
+             mode == 30 ? "zeros, one stage" : mode == 31 ? "random data, one stage" : mode == 32 ? "random data, 6-stage ring" :
+             mode == 33 ? "ring + 8 warps spinning on try_wait" : "ring + 8 warps in one long try_wait", s / 74 / 4000);
+    }
+  }
   return 0;
 }

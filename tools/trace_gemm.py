@@ -11,7 +11,7 @@ import torch
 
 from instructany2pix_b200 import _lib
 
-_lib.LIB_PATH = os.path.join(ROOT, "tools", "libia2p_trace.so")
+_lib.LIB_PATH = os.environ.get("IA2P_TRACE_LIB") or os.path.join(ROOT, "tools", "libia2p_trace.so")
 from instructany2pix_b200 import ops  # noqa: E402
 
 lib = _lib.load()
@@ -21,7 +21,7 @@ trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 lib.ia2p_debug_set_trace(trace.data_ptr())
 
 
-def run(name, fn):
+def run(name, fn, kb=0):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -40,7 +40,8 @@ def run(name, fn):
           f"setup {(t[act, 1] - t[act, 0]).mean().item() / 1e3:4.1f} us, body {(t[act, 8] - t[act, 1]).mean().item() / 1e3:6.1f} us, "
           f"last end {(t[:, 8].max() - t0) / 1e3:6.1f} us | tiles/CTA {f(9):4.1f} | MMA warp: loop {f(4) / 1e3:7.1f} kclk, "
           f"wait data {100 * f(2) / f(4):4.1f}%, wait epilogue {100 * f(3) / f(4):4.1f}% | producer wait-empty {f(5) / 1e3:7.1f} kclk | "
-          f"epilogue w2: wait acc {f(6) / 1e3:7.1f} kclk, busy {f(7) / 1e3:7.1f} kclk | ~{clk:.2f} GHz")
+          f"epilogue w2: wait acc {f(6) / 1e3:7.1f} kclk, busy {f(7) / 1e3:7.1f} kclk | ~{clk:.2f} GHz"
+          + (f" | {f(4) / (f(9) * kb):6.1f} clk per k-block" if kb else ""))
 
 
 def main():
@@ -58,7 +59,7 @@ def main():
             fn = lambda: ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, want_ln=True)
         else:
             fn = lambda: ops.gemm(a, w)
-        run(f"{name} M{M} N{N} K{K}", fn)
+        run(f"{name} M{M} N{N} K{K}", fn, K // 64)
 
 
 if __name__ == "__main__":
