@@ -52,7 +52,7 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
   const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, k_empty = bars + 40, v_empty = bars + 56;
   const uint32_t s_full = bars + 72, s_empty = bars + 80, p_full = bars + 88, pv_full = bars + 96, tmem_slot = bars + 104;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int n_blocks = (n_tokens + 127) >> 7;
 
@@ -76,7 +76,7 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, kFaTile);
       tma_load_3d(sQ, &maps.q, q_full, h * 64, q0, b);
     }
@@ -84,12 +84,12 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       const int st = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
       mbar_wait(k_empty + 8 * st, ph ^ 1u);
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(k_full + 8 * st, kFaTile);
         tma_load_3d(sK + st * kFaTile, &maps.k, k_full + 8 * st, h * 64, j * 128, b);
       }
       mbar_wait(v_empty + 8 * st, ph ^ 1u);
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(v_full + 8 * st, kFaTile);
         tma_load_3d(sV + st * kFaTile, &maps.v, v_full + 8 * st, h * 64, j * 128, b);
       }
@@ -113,7 +113,7 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       if (j > 0) mbar_wait(s_empty, (uint32_t)((j - 1) & 1));     // softmax finished reading S_{j-1}
       TRACE_ADD(tr_wait_sempty, tb);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t da = umma_desc_sw128(sQ), db = umma_desc_sw128(sK + st * kFaTile);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tS, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, (uint32_t)(k != 0));
@@ -134,7 +134,7 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       mbar_wait(p_full, (uint32_t)(j & 1));                       // P_j in smem; O (TMEM) rescaled if needed
       TRACE_ADD(tr_wait_p, td);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {                          // 8 x 16 keys = 8 TMEM columns of P each
           const uint64_t db = umma_desc_sw128_mn(sV + st * kFaTile + ks * 2048, kFaTile);

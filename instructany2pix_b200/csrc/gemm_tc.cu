@@ -714,12 +714,31 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       // consumer side of the LN fold: this row's mean / rstd from the producer's partial sums (fixed order: reproducible)
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (p.ln_stats != nullptr && valid) {
-        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + pix * p.ln_parts;
+        // All partials of the row are requested before the first add: issued one by one inside a run-time loop, the ~20 dependent
+        // L2 round trips (8 k cycles) made the epilogue of every LN-folded GEMM longer than its main loop (MMA warp waiting for a
+        // free accumulator 24-31 % of the QKV / GEGLU launches, profiles/README.md).  Same summation order as before.
+        const float* sp = p.ln_stats + pix * (long long)p.ln_parts * 2;
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < p.ln_parts; ++i) {
-          const float2 v = __ldg(sp + i);
-          s1 += v.x;
-          s2 += v.y;
+        if ((p.ln_parts & 3) == 0) {                        // 4 partials = one 32-byte sector (ia2p_gemm_ln_parts: 4 per N tile)
+          const int nq = p.ln_parts >> 2;
+          for (int i0 = 0; i0 < nq; i0 += 3) {
+            float v[3][8];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (i0 + j < nq) ldg256(sp + (i0 + j) * 8, v[j]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (i0 + j < nq) {
+                s1 += v[j][0]; s2 += v[j][1]; s1 += v[j][2]; s2 += v[j][3];
+                s1 += v[j][4]; s2 += v[j][5]; s1 += v[j][6]; s2 += v[j][7];
+              }
+          }
+        } else {
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(sp) + i);
+            s1 += v.x;
+            s2 += v.y;
+          }
         }
         ln_mean = s1 * p.ln_inv_n;
         ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_n - ln_mean * ln_mean, 0.f) + p.ln_eps);
@@ -1296,6 +1315,8 @@ extern "C" int ia2p_gemm_ln_bf16(const void* A, int64_t lda, int64_t K1, const v
   if (int e = check_device()) return e;
   IA2P_REQUIRE((ln_stats == nullptr) == (ln_c1 == nullptr) && (ln_stats == nullptr || (ln_parts > 0 && ln_parts <= 256)), IA2P_E_ARG,
                "gemm: ln_stats, ln_c1 and ln_parts must be given together");
+  IA2P_REQUIRE(ln_stats == nullptr || (ln_parts % 4 != 0) || (reinterpret_cast<uintptr_t>(ln_stats) & 31) == 0, IA2P_E_ALIGN,
+               "gemm: ln_stats must be 32-byte aligned");
   IA2P_REQUIRE((out_bf16 == nullptr && stats_out == nullptr) || epilogue != IA2P_EPI_GEGLU, IA2P_E_ARG,
                "gemm: the GEGLU epilogue cannot also produce LN statistics");
   IA2P_REQUIRE(out_bf16 == nullptr || ((reinterpret_cast<uintptr_t>(out_bf16) & 31) == 0 && ldo2 % 16 == 0), IA2P_E_ALIGN,

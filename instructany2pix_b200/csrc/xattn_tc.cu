@@ -47,7 +47,7 @@ xattn_tc_kernel(const __grid_constant__ XaMaps maps, int n_q, int n_text, int n_
   const uint32_t bars = raw;
   const uint32_t full = bars, empty = bars + 16, s_full = bars + 32, s_empty = bars + 40, p_full = bars + 48, o_full = bars + 56,
                  tmem_slot = bars + 64;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int n_qtiles = (n_q + 127) >> 7;
 
   if (warp == 0 && lane == 0) {
@@ -72,7 +72,7 @@ xattn_tc_kernel(const __grid_constant__ XaMaps maps, int n_q, int n_text, int n_
       const int st = it & 1;
       const int qt = w % n_qtiles, bh = w / n_qtiles, h = bh % heads, b = bh / heads;
       mbar_wait(empty + 8 * st, (uint32_t)(((it >> 1) & 1) ^ 1));
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sQ = tiles + st * STAGE, sK = sQ + kXaQ, sV = sK + KV;
         mbar_arrive_expect_tx(full + 8 * st, STAGE);
         tma_load_3d(sQ, &maps.q, full + 8 * st, h * 64, qt * 128, b);
@@ -95,7 +95,7 @@ xattn_tc_kernel(const __grid_constant__ XaMaps maps, int n_q, int n_text, int n_
       mbar_wait(full + 8 * st, (uint32_t)((it >> 1) & 1));
       if (it > 0) mbar_wait(s_empty, (uint32_t)((it - 1) & 1));              // softmax finished reading S of the previous item
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sQ = tiles + st * STAGE;
         const uint64_t da = umma_desc_sw128(sQ), db = umma_desc_sw128(sQ + kXaQ);
 #pragma unroll
@@ -110,7 +110,7 @@ xattn_tc_kernel(const __grid_constant__ XaMaps maps, int n_q, int n_text, int n_
       const int st = it & 1;
       mbar_wait(p_full, (uint32_t)(it & 1));                                  // P written; O of the previous item read out
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sV = tiles + st * STAGE + kXaQ + KV;
 #pragma unroll
         for (int ks = 0; ks < TK / 16; ++ks)

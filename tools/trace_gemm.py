@@ -47,13 +47,21 @@ def run(name, fn, kb=0):
 def main():
     torch.manual_seed(0)
     M = 8192
-    for name, N, K, mode in [("geglu 1280", 10240, 1280, "geglu"), ("ff_out 1280", 1280, 5120, "res"), ("qkv 1280", 3840, 1280, "plain"),
-                             ("out_proj 1280", 1280, 1280, "res"), ("to_q 1280", 1280, 1280, "plain"), ("square", 8192, 8192, "plain")]:
+    st = torch.rand(M, 20, 2, device=dev) + 1.0                     # LN partial sums as a 1280-wide producer emits them (4 per N tile)
+    for name, N, K, mode in [("geglu 1280", 10240, 1280, "geglu"), ("geglu 1280 ln-fold", 10240, 1280, "geglu_ln"), ("ff_out 1280", 1280, 5120, "res"),
+                             ("qkv 1280", 3840, 1280, "plain"), ("qkv 1280 ln-fold", 3840, 1280, "ln"),
+                             ("out_proj 1280", 1280, 1280, "res"), ("to_q 1280", 1280, 1280, "plain"), ("to_q 1280 ln-fold", 1280, 1280, "ln"),
+                             ("square", 8192, 8192, "plain")]:
         a = torch.randn(M, K, device=dev).to(BF)
         w = (torch.randn(N, K, device=dev) * K ** -0.5).to(BF)
         bias = torch.randn(N, device=dev)
+        c1 = torch.randn(N, device=dev)
         if mode == "geglu":
             fn = lambda: ops.gemm(a, w, bias=bias, geglu=True)
+        elif mode == "geglu_ln":
+            fn = lambda: ops.gemm(a, w, bias=bias, geglu=True, ln=(st, c1, 1e-5))
+        elif mode == "ln":
+            fn = lambda: ops.gemm(a, w, bias=bias, ln=(st, c1, 1e-5))
         elif mode == "res":
             res = torch.randn(M, N, device=dev)
             fn = lambda: ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, want_ln=True)
