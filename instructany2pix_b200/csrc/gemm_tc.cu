@@ -26,6 +26,9 @@
 // were measured slower than / equal to one narrow tile per CTA (profiles/README.md section 9), and merely compiling their
 // run-time branches into the kernel cost the batch-1 512^2 step 7 % (14.0 vs 13.0 ms, same box): hence compiled out.
 // ia2p_tc_features() reports what a build contains (bit 0 split-K, bit 1 multicast).
+#ifndef IA2P_EPI3_SLOTS
+#define IA2P_EPI3_SLOTS 2   // staging slots per epilogue half-group of the bf16 TMA-store epilogue (1: one more main-loop stage)
+#endif
 #ifndef IA2P_MAX_STAGES
 #define IA2P_MAX_STAGES 6   // smem ring depth cap (experiments: make variant NAME=.. DEFS=-DIA2P_MAX_STAGES=..)
 #endif
@@ -127,6 +130,11 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcParams& p, int item, in
 // SM (tools/membench.cu: one sector per lane per instruction), which made the fp32 residual GEMMs epilogue-bound.  Here the
 // two epilogue half-groups (4 warps = 128 rows each) stage 16-column slices in swizzled shared memory and one elected
 // thread per half-group hands them to the TMA store engine.
+// EPI = 3 (bf16 outputs without residual: QKV, to_q, GEGLU projections): the same idea for bf16 -- each half-group stages whole
+// 64-column output slices (128 rows x 128 B, SWIZZLE_128B; a 32-column remainder as SWIZZLE_64B) and hands them to the TMA store
+// engine.  Thread-per-row register stores (EPI 0) write one 32-byte sector per lane and instruction, ~12 B/clk per SM: 5 k cycles
+// for the 64 KB of a 128 x 256 bf16 tile, and with the LayerNorm fold on top the epilogue took longer than the tile's main loop
+// once the MMAs ran at the tensor-pipe rate (MMA warp waiting for a free accumulator 31 % of a QKV launch, profiles/README.md).
 // EPI = 2 (fp32 residual GEMMs with a short K: attention out-projections): additionally the residual slices arrive by TMA
 // load, two chunks ahead, into a 4-deep ring of the same staging slices (the thread reads its row, adds, and writes the
 // result back in place); the main loop gives up one stage for the ring.  With register loads the residual reads (a sector
@@ -139,7 +147,9 @@ struct TcCfg {
   static constexpr int BAR_BYTES = EPI ? 1024 : 256;
   static constexpr int EPI_F_BYTES = 128 * 64, EPI_H_BYTES = 128 * 32;          // per half-group: fp32 / bf16 16-column slice
   static constexpr int NBF = (EPI == 2) ? 4 : 1, NBH = (EPI == 2) ? 2 : 1;       // staging ring depth per half-group
-  static constexpr int EPI_BYTES = EPI ? 2 * (NBF * EPI_F_BYTES + NBH * EPI_H_BYTES) : 0;
+  static constexpr int EPI3_SLICE = 128 * 128;                                   // EPI 3: 128 rows x 64 bf16 columns, EPI3_SLOTS slots per half-group
+  static constexpr int EPI3_SLOTS = IA2P_EPI3_SLOTS;
+  static constexpr int EPI_BYTES = EPI == 3 ? 2 * EPI3_SLOTS * EPI3_SLICE : EPI ? 2 * (NBF * EPI_F_BYTES + NBH * EPI_H_BYTES) : 0;
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - BAR_BYTES - EPI_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > IA2P_MAX_STAGES ? IA2P_MAX_STAGES : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -439,6 +449,183 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     TRACE_PUT(3, tr_wait_tempty);
     TRACE_PUT(4, tr_loop);
     TRACE_PUT(9, it);
+  } else if (EPI == 3) {
+    // ------------------------------------------------------------ epilogue, bf16 output through shared memory + TMA store
+    // Half-group h = warps {2..5} / {6..9} (each covers the tile's 128 rows) owns the 64-column OUTPUT slices h, h + 2, ...; a
+    // thread turns its row's accumulator columns of the slice into bf16 (bias / row bias / LN fold / GEGLU), writes them into the
+    // half-group's swizzled staging slot, and the elected thread issues one TMA store per slice (two slots: one drains while the
+    // next is filled).  The two half-groups never synchronise with each other.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const bool elected = (warp == 2 + 4 * half) && lane == 0;
+    const int tw = row & ((1 << p.tw_log2) - 1);
+    const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+    const int tb = row >> (p.tw_log2 + p.th_log2);
+    const uint32_t st_base = smem_base + Cfg::STAGE_OFF + half * (Cfg::EPI3_SLOTS * Cfg::EPI3_SLICE);
+    const uint32_t sw128 = (uint32_t)row & 7u;             // SWIZZLE_128B: 16-B chunk ^= row % 8
+    const uint32_t sw64 = (uint32_t)(row >> 1) & 3u;       // SWIZZLE_64B (32-column remainder slice): 16-B chunk ^= (row / 2) % 4
+    const uint32_t tempty_leader0 = (CG == 2 && rank != 0) ? mapa_shared(tempty_bar(0), 0) : 0u;
+    int it = 0;
+    TRACE_DECL(tr_wait_tfull);
+    TRACE_DECL(tr_busy);
+    uint32_t g = 0;                                        // slices stored so far by this half-group (slot = g & 1)
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
+      const int m_tile = ti.m_unit * CG + (int)rank;
+      const int xt = m_tile % p.tiles_x;
+      const int r = m_tile / p.tiles_x;
+      const int yt = r % p.tiles_y, bt = r / p.tiles_y;
+      const int x0 = xt << p.tw_log2, y0 = yt << p.th_log2, b0 = bt * TB;
+      const int x = x0 + tw, y = y0 + th, b = b0 + tb;
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B) && (m_tile < p.m_tiles);
+      const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+      const int n_base = ti.n_tile * BLOCK_N + ti.n_off;    // first accumulator column (index into N) of this item
+      int aw = ti.w;                                        // accumulator columns of this item that exist
+      if (p.N - n_base < aw) aw = p.N - n_base;
+      const int ow = p.geglu ? aw >> 1 : aw;                // output columns, and the first one
+      const int o_base = p.geglu ? n_base >> 1 : n_base;
+      const int nsl = (ow + 63) >> 6;
+      const float* rb = (p.rowbias != nullptr && valid) ? p.rowbias + (pix / p.rows_per_batch) * (long long)p.N : nullptr;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats != nullptr && valid) {                 // LN-fold consumer: see the EPI 0 epilogue
+        const float* sp = p.ln_stats + pix * (long long)p.ln_parts * 2;
+        float s1 = 0.f, s2 = 0.f;
+        if ((p.ln_parts & 3) == 0) {
+          const int nq = p.ln_parts >> 2;
+          for (int i0 = 0; i0 < nq; i0 += 3) {
+            float v[3][8];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (i0 + j < nq) ldg256(sp + (i0 + j) * 8, v[j]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (i0 + j < nq) {
+                s1 += v[j][0]; s2 += v[j][1]; s1 += v[j][2]; s2 += v[j][3];
+                s1 += v[j][4]; s2 += v[j][5]; s1 += v[j][6]; s2 += v[j][7];
+              }
+          }
+        } else {
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(sp) + i);
+            s1 += v.x;
+            s2 += v.y;
+          }
+        }
+        ln_mean = s1 * p.ln_inv_n;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_n - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
+      const float ln_nm = -ln_mean * ln_rstd;               // rstd * (acc - mean * c1) + bias = acc * rstd + (c1 * (-mean * rstd) + bias)
+
+      TRACE_T0(tq0);
+      mbar_wait(tfull_bar(buf), use & 1u);
+      TRACE_ADD(tr_wait_tfull, tq0);
+      TRACE_T0(tb0);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N);
+      auto release_acc = [&]() {                            // after this warp's last TMEM read of the item
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2 && rank != 0) mbar_arrive_cluster(tempty_leader0 + 8u * buf);
+          else mbar_arrive(tempty_bar(buf));
+        }
+      };
+      if (half >= nsl) release_acc();                       // nothing to read for this half-group
+
+#pragma unroll 1
+      for (int sl = half; sl < nsl; sl += 2) {
+        const int cols = (ow - 64 * sl) < 64 ? (ow - 64 * sl) : 64;      // 64, or 32 for a remainder slice
+        const uint32_t slot = st_base + (Cfg::EPI3_SLOTS > 1 ? (g & 1u) * Cfg::EPI3_SLICE : 0u);
+        uint32_t pk[32];                                                 // this row's slice: 64 bf16
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {
+          if (pc * 32 < cols) {                                          // uniform over the half-group
+            const int oc = 64 * sl + 32 * pc;                            // output column (within the item) of this 32-column piece
+            float f[32];
+            if (!p.geglu) {
+              const int n = n_base + oc;
+              uint32_t v[32];
+              tmem_ld_32x32(t_row + (uint32_t)oc, v);
+              tmem_ld_wait();
+              if (sl + 2 >= nsl && (pc + 1) * 32 >= cols) release_acc();
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                if (p.ln_stats != nullptr) {
+                  const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + i));
+                  bv.x = fmaf(cv.x, ln_nm, bv.x); bv.y = fmaf(cv.y, ln_nm, bv.y); bv.z = fmaf(cv.z, ln_nm, bv.z); bv.w = fmaf(cv.w, ln_nm, bv.w);
+                }
+                if (rb != nullptr) {
+                  const float4 rv = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+                  bv.x += rv.x; bv.y += rv.y; bv.z += rv.z; bv.w += rv.w;
+                }
+                f[i] = fmaf(__uint_as_float(v[i]), ln_rstd, bv.x); f[i + 1] = fmaf(__uint_as_float(v[i + 1]), ln_rstd, bv.y);
+                f[i + 2] = fmaf(__uint_as_float(v[i + 2]), ln_rstd, bv.z); f[i + 3] = fmaf(__uint_as_float(v[i + 3]), ln_rstd, bv.w);
+              }
+            } else {
+              // GEGLU: accumulator columns come in 64-wide groups [32 value | 32 gate] (W rows interleaved, packing.interleave_geglu)
+              const int n = n_base + 2 * oc;
+              uint32_t vv[32], vg[32];
+              tmem_ld_32x32(t_row + (uint32_t)(2 * oc), vv);
+              tmem_ld_32x32(t_row + (uint32_t)(2 * oc + 32), vg);
+              tmem_ld_wait();
+              if (sl + 2 >= nsl && (pc + 1) * 32 >= cols) release_acc();
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+                if (p.bias != nullptr) {
+                  bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                  bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32 + i));
+                }
+                if (p.ln_stats != nullptr) {
+                  const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + i));
+                  const float4 cg = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + n + 32 + i));
+                  bv.x = fmaf(cv.x, ln_nm, bv.x); bv.y = fmaf(cv.y, ln_nm, bv.y); bv.z = fmaf(cv.z, ln_nm, bv.z); bv.w = fmaf(cv.w, ln_nm, bv.w);
+                  bg.x = fmaf(cg.x, ln_nm, bg.x); bg.y = fmaf(cg.y, ln_nm, bg.y); bg.z = fmaf(cg.z, ln_nm, bg.z); bg.w = fmaf(cg.w, ln_nm, bg.w);
+                }
+                f[i + 0] = fmaf(__uint_as_float(vv[i + 0]), ln_rstd, bv.x) * gelu_erf_f(fmaf(__uint_as_float(vg[i + 0]), ln_rstd, bg.x));
+                f[i + 1] = fmaf(__uint_as_float(vv[i + 1]), ln_rstd, bv.y) * gelu_erf_f(fmaf(__uint_as_float(vg[i + 1]), ln_rstd, bg.y));
+                f[i + 2] = fmaf(__uint_as_float(vv[i + 2]), ln_rstd, bv.z) * gelu_erf_f(fmaf(__uint_as_float(vg[i + 2]), ln_rstd, bg.z));
+                f[i + 3] = fmaf(__uint_as_float(vv[i + 3]), ln_rstd, bv.w) * gelu_erf_f(fmaf(__uint_as_float(vg[i + 3]), ln_rstd, bg.w));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[16 * pc + i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+          }
+        }
+        // the slot must have been read out by its previous store (two slices ago): at most one group may still be pending
+        if (elected) {
+          if (Cfg::EPI3_SLOTS > 1) bulk_wait_read_1(); else bulk_wait_read_all();
+        }
+        named_bar_sync(1 + half, 128);
+        if (cols == 64) {
+          const uint32_t d = slot + (uint32_t)row * 128u;
+#pragma unroll
+          for (uint32_t j = 0; j < 8; ++j) sts128u(d + ((j ^ sw128) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else {
+          const uint32_t d = slot + (uint32_t)row * 64u;
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) sts128u(d + ((j ^ sw64) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + half, 128);
+        if (elected) {
+          tma_store_4d(cols == 64 ? &maps.o : &maps.o2, slot, o_base + 64 * sl, x0, y0, b0);   // rows / columns outside the output are clipped
+          bulk_commit_group();
+        }
+        ++g;
+      }
+      TRACE_ADD(tr_busy, tb0);
+    }
+    if (elected) bulk_wait_read_all();                          // staging memory must outlive the last store's read
+    if (warp == 2) { TRACE_PUT(6, tr_wait_tfull); TRACE_PUT(7, tr_busy); }
+#ifdef IA2P_TC_TRACE
+    if (warp == 2) TRACE_PUT(11, gtime_ns());                          // this CTA's epilogue is done
+#endif
   } else if (EPI >= 1) {
     // ------------------------------------------------------------ epilogue, TMA variants (fp32 out [+ bf16 copy + LN stats])
     // Half-group h = warps {2..5} / {6..9} owns columns [32 c + 16 h, +16) of every 32-column chunk c of the tile: per chunk
@@ -1128,7 +1315,12 @@ static bool use_pair(int m_tiles, int num_kb, int64_t N, int bn) {
   if (m_tiles < 2 || bn == 64) return false;                      // BLOCK_N 64 exists for small problems only: single CTA
   if (pick_ksplit((int64_t)m_tiles * ((N + bn - 1) / bn), num_kb, bn) > 1) return false;   // split-K runs on the single-CTA kernel
   if (v == 0 && (int64_t)m_tiles * ((N + bn - 1) / bn) < 2 * sm_count()) return false;   // too few tiles to pair up
-  return v == 2 || (v == 0 && num_kb > 12);
+  static int min_kb = -1;
+  if (min_kb < 0) {
+    const char* e = getenv("IA2P_GEMM_PAIR_MINKB");      // experiments: pairs from this many k-blocks on (default 13)
+    min_kb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 13;
+  }
+  return v == 2 || (v == 0 && num_kb >= min_kb);
 }
 
 // A-operand multicast (TcParams::mc), OPT-IN (IA2P_GEMM_MC=2 | 4 = largest cluster): for problems that fit in ONE wave of
@@ -1184,9 +1376,24 @@ static bool tma_residual(const TcParams& p) {
   return v != 0 && tma_epilogue(p) && p.residual != nullptr && p.res_f32 && p.num_kb <= 24;
 }
 
+// bf16 outputs without residual / LN-producer extras go through the TMA-store epilogue (EPI = 3); IA2P_GEMM_EPI3=0 keeps them on the
+// register-store epilogue (experiments)
+static bool tma_epilogue_bf16(const TcParams& p) {
+#ifdef IA2P_WITH_SPLITK
+  return false;                                          // the split-K fix-up pass lives in the EPI 0 / 1 epilogues only
+#endif
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IA2P_GEMM_EPI3");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0 && !p.out_f32 && p.residual == nullptr && p.out2 == nullptr && p.stats_out == nullptr && p.colstats == nullptr;
+}
+
 template <int BN>
 static int dispatch_bn(const TcMaps& maps, TcParams& p, cudaStream_t st) {
   const bool pair = use_pair(p.m_tiles, p.num_kb, p.N, BN);
+  if (tma_epilogue_bf16(p)) return pair ? launch_tc<BN, 2, 3>(maps, p, st) : launch_tc<BN, 1, 3>(maps, p, st);
   if (tma_residual(p)) return pair ? launch_tc<BN, 2, 2>(maps, p, st) : launch_tc<BN, 1, 2>(maps, p, st);
   if (tma_epilogue(p)) return pair ? launch_tc<BN, 2, 1>(maps, p, st) : launch_tc<BN, 1, 1>(maps, p, st);
   return pair ? launch_tc<BN, 2, 0>(maps, p, st) : launch_tc<BN, 1, 0>(maps, p, st);
@@ -1211,6 +1418,20 @@ static int dispatch_tc(TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
       const uint64_t strr[4] = {1, (uint64_t)p.ldr, (uint64_t)p.ldr * p.Wo, (uint64_t)p.ldr * p.Wo * p.Ho};
       if (int e = make_map(&maps.r, p.residual, 4, dims, strr, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     }
+  } else if (tma_epilogue_bf16(p)) {
+    // bf16 output maps: the A operand's pixel-box geometry, 64 columns (SWIZZLE_128B) and 32 columns (remainder slice, SWIZZLE_64B)
+    const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TB = 128 >> (p.tw_log2 + p.th_log2);
+    const uint64_t n_out = (uint64_t)(p.geglu ? p.N / 2 : p.N);
+    const uint64_t dims[4] = {n_out, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
+    const uint64_t str[4] = {1, (uint64_t)(p.ost_x ? p.ost_x : p.ldo), (uint64_t)(p.ost_y ? p.ost_y : p.ldo * p.Wo),
+                             (uint64_t)(p.ost_b ? p.ost_b : p.ldo * p.Wo * p.Ho)};
+    const uint32_t box64[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB}, box32[4] = {32, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+    if (n_out >= 64) {
+      if (int e = make_map(&maps.o, p.out, 4, dims, str, box64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
+    if (int e = make_map(&maps.o2, p.out, 4, dims, str, box32, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    if (n_out < 64) maps.o = maps.o2;
+    maps.r = maps.o2;
   } else {
     maps.o = maps.w;                 // unused: keep the kernel parameter defined
     maps.o2 = maps.w;
@@ -1220,6 +1441,7 @@ static int dispatch_tc(TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
     case 256: return dispatch_bn<256>(maps, p, st);
     case 160: return dispatch_bn<160>(maps, p, st);
     case 64:
+      if (tma_epilogue_bf16(p)) return launch_tc<64, 1, 3>(maps, p, st);
       if (tma_residual(p)) return launch_tc<64, 1, 2>(maps, p, st);
       if (tma_epilogue(p)) return launch_tc<64, 1, 1>(maps, p, st);
       return launch_tc<64, 1, 0>(maps, p, st);

@@ -159,6 +159,22 @@ def test_few_row_problems(kind, path, monkeypatch):
         assert torch.equal(tb, t.to(torch.bfloat16)) and rel(st.sum(1)[:, 0], t.sum(1)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N", [(200, 96), (384, 160), (1000, 224), (128, 32)])
+def test_gemm_bf16_tma_store_ragged_widths(M, N):
+    """bf16 outputs leave through 64-column TMA-store slices (EPI 3): widths with a 32-column remainder slice, rows past M and a
+    row-strided destination must neither lose nor spill a column; bias + per-image row bias applied in the same epilogue."""
+    K = 128
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias = rnd(N, dtype=torch.float32)
+    rpb = 8
+    rowbias = rnd((M + rpb - 1) // rpb, N, dtype=torch.float32)
+    buf = torch.full((M + 3, N + 64), 7.0, device=DEV, dtype=torch.bfloat16)
+    out = ops.gemm(a, w, bias=bias, rowbias=rowbias, rows_per_batch=rpb, out=buf[:M, 32:32 + N])
+    ref = a.float() @ w.float().t() + bias + rowbias.repeat_interleave(rpb, 0)[:M]
+    assert rel(out, ref) < TOL
+    assert (buf[:M, :32] == 7.0).all() and (buf[:M, 32 + N:] == 7.0).all() and (buf[M:] == 7.0).all()
+
+
 def test_gemm_epilogues():
     M, N, K = 768, 640, 320
     a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
