@@ -128,25 +128,29 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcParams& p, int item, in
 // EPI = 0: the epilogue stores straight from registers (bf16 outputs: 64 KB per tile, far below what the LSU path moves).
 // EPI = 1 (fp32 outputs, optionally + bf16 copy: 192 KB per tile): thread-per-row register stores top out near 23 GB/s per
 // SM (tools/membench.cu: one sector per lane per instruction), which made the fp32 residual GEMMs epilogue-bound.  Here the
-// two epilogue half-groups (4 warps = 128 rows each) stage 16-column slices in swizzled shared memory and one elected
-// thread per half-group hands them to the TMA store engine.
+// two epilogue half-groups (4 warps = 128 rows each) stage 32-column slices in swizzled shared memory and one elected
+// lane per half-group hands them to the TMA store engine.
 // EPI = 3 (bf16 outputs without residual: QKV, to_q, GEGLU projections): the same idea for bf16 -- each half-group stages whole
 // 64-column output slices (128 rows x 128 B, SWIZZLE_128B; a 32-column remainder as SWIZZLE_64B) and hands them to the TMA store
 // engine.  Thread-per-row register stores (EPI 0) write one 32-byte sector per lane and instruction, ~12 B/clk per SM: 5 k cycles
 // for the 64 KB of a 128 x 256 bf16 tile, and with the LayerNorm fold on top the epilogue took longer than the tile's main loop
 // once the MMAs ran at the tensor-pipe rate (MMA warp waiting for a free accumulator 31 % of a QKV launch, profiles/README.md).
 // EPI = 2 (fp32 residual GEMMs with a short K: attention out-projections): additionally the residual slices arrive by TMA
-// load, two chunks ahead, into a 4-deep ring of the same staging slices (the thread reads its row, adds, and writes the
-// result back in place); the main loop gives up one stage for the ring.  With register loads the residual reads (a sector
-// per lane per instruction, 2 chunks of prefetch) were the critical path of those GEMMs (profiles/README.md).
+// load, one slice ahead, into the second of two fp32 staging slots (the thread reads its row, adds, and writes the result
+// back in place); the main loop gives up two stages for them.  With register loads the residual reads (a sector per lane
+// per instruction) were the critical path of those GEMMs (profiles/README.md).
 template <int BLOCK_N, int CG = 1, int EPI = 0>
 struct TcCfg {
   static constexpr int A_BYTES = 128 * 128;             // 128 rows x 64 bf16
   static constexpr int B_BYTES = (BLOCK_N / CG) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = EPI ? 1024 : 256;
-  static constexpr int EPI_F_BYTES = 128 * 64, EPI_H_BYTES = 128 * 32;          // per half-group: fp32 / bf16 16-column slice
-  static constexpr int NBF = (EPI == 2) ? 4 : 1, NBH = (EPI == 2) ? 2 : 1;       // staging ring depth per half-group
+  // fp32-output epilogues: slice width per half-group and round.  EPI 2 (short K: the epilogue is the critical path) moves 32
+  // columns per round -- half the barrier / TMA round trips per tile; EPI 1 (long K: the main loop is) keeps 16-column slices and
+  // their smaller staging buffers (one more main-loop stage: measured, 6 vs 5 stages is worth 3-6 % on the K >= 2560 shapes).
+  static constexpr int SLW = (EPI == 2) ? 32 : 16;
+  static constexpr int EPI_F_BYTES = 128 * SLW * 4, EPI_H_BYTES = 128 * SLW * 2; // per half-group: fp32 / bf16 slice
+  static constexpr int NBF = (EPI == 2) ? 2 : 1, NBH = 1;                        // fp32 slots per half-group (EPI 2: one holds the next residual)
   static constexpr int EPI3_SLICE = 128 * 128;                                   // EPI 3: 128 rows x 64 bf16 columns, EPI3_SLOTS slots per half-group
   static constexpr int EPI3_SLOTS = IA2P_EPI3_SLOTS;
   static constexpr int EPI_BYTES = EPI == 3 ? 2 * EPI3_SLOTS * EPI3_SLICE : EPI ? 2 * (NBF * EPI_F_BYTES + NBH * EPI_H_BYTES) : 0;
@@ -458,7 +462,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const bool elected = (warp == 2 + 4 * half) && lane == 0;
+    const bool lead_warp = (warp == 2 + 4 * half);        // its elect.sync lane issues the half-group's TMA traffic (uniform operands)
     const int tw = row & ((1 << p.tw_log2) - 1);
     const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
     const int tb = row >> (p.tw_log2 + p.th_log2);
@@ -598,7 +602,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
         }
         // the slot must have been read out by its previous store (two slices ago): at most one group may still be pending
-        if (elected) {
+        if (lead_warp && elect_one()) {
           if (Cfg::EPI3_SLOTS > 1) bulk_wait_read_1(); else bulk_wait_read_all();
         }
         named_bar_sync(1 + half, 128);
@@ -613,7 +617,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         fence_proxy_async();
         named_bar_sync(1 + half, 128);
-        if (elected) {
+        if (lead_warp && elect_one()) {
           tma_store_4d(cols == 64 ? &maps.o : &maps.o2, slot, o_base + 64 * sl, x0, y0, b0);   // rows / columns outside the output are clipped
           bulk_commit_group();
         }
@@ -621,35 +625,41 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
       TRACE_ADD(tr_busy, tb0);
     }
-    if (elected) bulk_wait_read_all();                          // staging memory must outlive the last store's read
+    if (lead_warp && elect_one()) bulk_wait_read_all();                          // staging memory must outlive the last store's read
     if (warp == 2) { TRACE_PUT(6, tr_wait_tfull); TRACE_PUT(7, tr_busy); }
 #ifdef IA2P_TC_TRACE
     if (warp == 2) TRACE_PUT(11, gtime_ns());                          // this CTA's epilogue is done
 #endif
   } else if (EPI >= 1) {
     // ------------------------------------------------------------ epilogue, TMA variants (fp32 out [+ bf16 copy + LN stats])
-    // Half-group h = warps {2..5} / {6..9} owns columns [32 c + 16 h, +16) of every 32-column chunk c of the tile: per chunk
-    // each thread reads 16 accumulator columns of its row, applies bias / row bias / residual, writes the fp32 (and bf16)
-    // values into the half-group's swizzled staging slice, and the elected thread issues one TMA store per slice.  The two
-    // half-groups never synchronise with each other, so one slice drains while the other is being filled.
-    constexpr int NBF = Cfg::NBF, NBH = Cfg::NBH;
+    // Half-group h = warps {2..5} / {6..9} (each covers the tile's 128 rows) owns the SLW-column slices h, h + 2, ... of the item:
+    // per slice a thread reads its row's SLW (EPI 2: 32, EPI 1: 16) accumulator columns, applies bias / row bias / residual, writes the fp32 (and bf16)
+    // values into the half-group's swizzled staging slot (128 B rows, SWIZZLE_128B; bf16 copy 64 B rows, SWIZZLE_64B), and the
+    // half-group's elect.sync lane issues one TMA store per slot.  EPI 2: the residual slice of the NEXT slice is TMA-loaded into
+    // the other fp32 slot meanwhile and summed in place.  The two half-groups never synchronise with each other.
+    // (Round-2 history: with 16-column slices -- twice the barrier / TMA round trips per tile -- this epilogue needed 11 us per
+    // 128 x 256 tile against 7 us of MMAs, i.e. the 126 attention out-projections of a step were epilogue-bound.)
+    constexpr int NBF = Cfg::NBF, SLW = Cfg::SLW;
+    constexpr uint32_t NCF = SLW / 4, NCH = SLW / 8;      // 16-byte chunks per staged fp32 / bf16 row
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const bool elected = (warp == 2 + 4 * half) && lane == 0;
+    const bool lead_warp = (warp == 2 + 4 * half);        // its elect.sync lane issues the half-group's TMA traffic (uniform operands)
     const int tw = row & ((1 << p.tw_log2) - 1);
     const int th = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
     const int tb = row >> (p.tw_log2 + p.th_log2);
     const uint32_t st_f = smem_base + Cfg::STAGE_OFF + half * (NBF * Cfg::EPI_F_BYTES);
-    const uint32_t st_h = smem_base + Cfg::STAGE_OFF + 2 * NBF * Cfg::EPI_F_BYTES + half * (NBH * Cfg::EPI_H_BYTES);
-    const uint32_t sw64 = (uint32_t)(row >> 1) & 3u;      // SWIZZLE_64B: 16-B chunk ^= (row / 2) % 4
-    const uint32_t sw32 = (uint32_t)(row >> 2) & 1u;      // SWIZZLE_32B: 16-B chunk ^= (row / 4) % 2
-    auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + half * 4 + b); };
+    const uint32_t st_h = smem_base + Cfg::STAGE_OFF + 2 * NBF * Cfg::EPI_F_BYTES + half * Cfg::EPI_H_BYTES;
+    // swizzle of the staged rows: 128-byte rows SWIZZLE_128B (16-B chunk ^= row % 8), 64-byte rows SWIZZLE_64B (^= (row / 2) % 4),
+    // 32-byte rows SWIZZLE_32B (^= (row / 4) % 2)
+    const uint32_t swf = (SLW == 32) ? ((uint32_t)row & 7u) : ((uint32_t)(row >> 1) & 3u);
+    const uint32_t swh = (SLW == 32) ? ((uint32_t)(row >> 1) & 3u) : ((uint32_t)(row >> 2) & 1u);
+    auto res_full = [&](uint32_t b) { return bar_base + 8u * (uint32_t)(2 * STAGES + 6 + half * 4) + 8u * b; };
     const uint32_t tempty_leader0 = (CG == 2 && rank != 0) ? mapa_shared(tempty_bar(0), 0) : 0u;
     int it = 0;
     TRACE_DECL(tr_wait_tfull);
     TRACE_DECL(tr_busy);
-    uint32_t g = 0;                                       // chunks processed so far by this half-group (ring position)
+    uint32_t g = 0;                                       // slices processed so far by this half-group (EPI 2: ring position)
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -668,35 +678,33 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B) && (m_tile < p.m_tiles);
       const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
       const int n_base = ti.n_tile * BLOCK_N + ti.n_off;
-      const int n0 = n_base + 16 * half;                    // first column of this half-group's slice of chunk 0
-      int nch = ti.w >> 5;                                  // 32-column chunks of this item that exist in the output
-      if ((p.N - n_base) < ti.w) nch = (p.N - n_base) >> 5;
+      int nsl = ti.w / SLW;                                 // SLW-column slices of this item that exist in the output
+      if ((p.N - n_base) < ti.w) nsl = (p.N - n_base) / SLW;
       const float* rb = (p.rowbias != nullptr && valid) ? p.rowbias + (pix / p.rows_per_batch) * (long long)p.N : nullptr;
       const bool res32 = (EPI == 1) && (p.residual != nullptr) && p.res_f32 && valid;
       const bool res16 = (p.residual != nullptr) && !p.res_f32 && valid;
       const float* res_row = static_cast<const float*>(p.residual) + pix * p.ldr;
       float st_sum = 0.f, st_sq = 0.f;
 
-      auto issue_res = [&](int c, uint32_t gg) {            // elected thread, EPI == 2
-        const uint32_t bb = gg & 3u;
-        mbar_arrive_expect_tx(res_full((int)bb), Cfg::EPI_F_BYTES);
-        tma_load_4d(st_f + bb * Cfg::EPI_F_BYTES, &maps.r, res_full((int)bb), n0 + c * 32, x0, y0, b0);
+      auto issue_res = [&](int sl, uint32_t gg) {           // elected lane, EPI == 2: residual slice -> fp32 slot gg & 1
+        const uint32_t bb = gg & 1u;
+        mbar_arrive_expect_tx(res_full(bb), Cfg::EPI_F_BYTES);
+        tma_load_4d(st_f + bb * Cfg::EPI_F_BYTES, &maps.r, res_full(bb), n_base + sl * SLW, x0, y0, b0);
       };
-      float rpre[2][16];
-      auto load_res = [&](int c, float (&dst)[16]) {
-        ldg256(res_row + n0 + c * 32, &dst[0]);
-        ldg256(res_row + n0 + c * 32 + 8, &dst[8]);
+      float rpre[2][SLW];                                   // EPI 1: fp32 residual of the next two slices of this half-group
+      auto load_res = [&](int sl, float (&dst)[SLW]) {
+#pragma unroll
+        for (int i = 0; i < SLW / 8; ++i) ldg256(res_row + n_base + sl * SLW + i * 8, &dst[i * 8]);
       };
       if (EPI == 2) {
-        if (elected) {
-          bulk_wait_read_1();                               // every slice but the one stored last is free again
-          issue_res(0, g);
-          if (nch > 1) issue_res(1, g + 1);
+        if (half < nsl && lead_warp && elect_one()) {
+          bulk_wait_read_all();                             // both fp32 slots are free again
+          issue_res(half, g);
         }
       } else {
-        if (res32) {
-          load_res(0, rpre[0]);
-          if (nch > 1) load_res(1, rpre[1]);
+        if (res32 && half < nsl) {
+          load_res(half, rpre[0]);
+          if (half + 2 < nsl) load_res(half + 2, rpre[1]);
         }
         // pull the NEXT item's residual rows (this half-group's slices) into L2 while this one is processed
         if ((p.residual != nullptr) && p.res_f32 && tile + unit_step < total_tiles) {
@@ -708,7 +716,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const int x2 = (xt2 << p.tw_log2) + tw, y2 = (yt2 << p.th_log2) + th, b2 = bt2 * TB + tb;
           if ((x2 < p.Wo) && (y2 < p.Ho) && (b2 < p.B) && (m_tile2 < p.m_tiles)) {
             const long long pix2 = ((long long)b2 * p.Ho + y2) * p.Wo + x2;
-            const int col2 = ti2.n_tile * BLOCK_N + ti2.n_off + 16 * half;
+            const int col2 = ti2.n_tile * BLOCK_N + ti2.n_off + 16 * half;       // one 32-byte sector's line per 32 columns
             const float* rrow = static_cast<const float*>(p.residual) + pix2 * p.ldr + col2;
 #pragma unroll
             for (int i = 0; i < BLOCK_N / 32; ++i)
@@ -723,113 +731,121 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       TRACE_ADD(tr_wait_tfull, tq0);
       TRACE_T0(tb0);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + 16 * half);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N);
+      auto release_acc = [&]() {                            // after this warp's last TMEM read of the item
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2 && rank != 0) mbar_arrive_cluster(tempty_leader0 + 8u * buf);
+          else mbar_arrive(tempty_bar(buf));
+        }
+      };
+      if (half >= nsl) release_acc();                       // nothing to read for this half-group
 
+      // (fully unrolled over the slices a half-group can own: lets the compiler hoist the next slice's loads over the barriers)
 #pragma unroll
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        if (c < nch) {                                          // uniform over the half-group
-          const int n = n0 + c * 32;
-          const uint32_t f_row = st_f + (NBF > 1 ? (g & 3u) * Cfg::EPI_F_BYTES : 0u) + row * 64;
-          const uint32_t h_row = st_h + (NBH > 1 ? (g & 1u) * Cfg::EPI_H_BYTES : 0u) + row * 32;
-          uint32_t v[16];
-          tmem_ld_32x16(t_row + (uint32_t)(c * 32), v);
+      for (int k = 0; k < (BLOCK_N / SLW + 1) / 2; ++k) {
+        const int sl = half + 2 * k;
+        const int pi = k & 1;                               // rpre slot of this slice
+        if (sl >= nsl) break;                               // uniform over the half-group
+        const int n = n_base + sl * SLW;
+        const uint32_t f_slot = st_f + (NBF > 1 ? (g & 1u) * Cfg::EPI_F_BYTES : 0u);
+        const uint32_t f_row = f_slot + (uint32_t)row * (uint32_t)(SLW * 4);
+        const uint32_t h_row = st_h + (uint32_t)row * (uint32_t)(SLW * 2);
+        float f[SLW];
+        {
+          uint32_t v[SLW];
+          if constexpr (SLW == 32) tmem_ld_32x32(t_row + (uint32_t)(sl * SLW), v);
+          else tmem_ld_32x16(t_row + (uint32_t)(sl * SLW), v);
           tmem_ld_wait();
-          if (c == nch - 1) {                                   // last TMEM read of this item: release the accumulator early
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CG == 2 && rank != 0) mbar_arrive_cluster(tempty_leader0 + 8u * buf);
-              else mbar_arrive(tempty_bar(buf));
+          if (sl + 2 >= nsl) release_acc();                 // last TMEM read of this item: release the accumulator early
+#pragma unroll
+          for (int i = 0; i < SLW; ++i) f[i] = __uint_as_float(v[i]);
+        }
+        if (valid) {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < SLW; i += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+              f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
             }
           }
-          float f[16];
+          if (rb != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (valid) {
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-              }
-            }
-            if (rb != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + n + i));
-                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-              }
-            }
-            if (res32) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] += rpre[c & 1][i];
-              if (c + 2 < nch) load_res(c + 2, rpre[c & 1]);
-            } else if (res16) {
-              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + n);
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const uint4 rv = __ldg(rp + i);
-                float2 t;
-                t = unpack_bf16x2(rv.x); f[8 * i + 0] += t.x; f[8 * i + 1] += t.y;
-                t = unpack_bf16x2(rv.y); f[8 * i + 2] += t.x; f[8 * i + 3] += t.y;
-                t = unpack_bf16x2(rv.z); f[8 * i + 4] += t.x; f[8 * i + 5] += t.y;
-                t = unpack_bf16x2(rv.w); f[8 * i + 6] += t.x; f[8 * i + 7] += t.y;
-              }
+            for (int i = 0; i < SLW; i += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+              f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
             }
           }
-          // staging slices of this chunk must be free: EPI 1 -> the previous store has been read out; EPI 2 -> all but the
-          // previous one (ring), which also frees the slice that receives the residual of chunk c + 2
-          if (elected) {
-            if (EPI == 2) {
-              bulk_wait_read_1();
-              if (c + 2 < nch) issue_res(c + 2, g + 2);
-            } else {
-              bulk_wait_read_all();
+          if (res32) {
+#pragma unroll
+            for (int i = 0; i < SLW; ++i) f[i] += rpre[pi][i];
+            if (sl + 4 < nsl) load_res(sl + 4, rpre[pi]);
+          } else if (res16) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + n);
+#pragma unroll
+            for (int i = 0; i < SLW / 8; ++i) {
+              const uint4 rv = __ldg(rp + i);
+              float2 t;
+              t = unpack_bf16x2(rv.x); f[8 * i + 0] += t.x; f[8 * i + 1] += t.y;
+              t = unpack_bf16x2(rv.y); f[8 * i + 2] += t.x; f[8 * i + 3] += t.y;
+              t = unpack_bf16x2(rv.z); f[8 * i + 4] += t.x; f[8 * i + 5] += t.y;
+              t = unpack_bf16x2(rv.w); f[8 * i + 6] += t.x; f[8 * i + 7] += t.y;
             }
           }
-          named_bar_sync(1 + half, 128);
-          if (EPI == 2) {
-            mbar_wait(res_full((int)(g & 3u)), (g >> 2) & 1u);
+        }
+        // every store issued so far must have been read out of shared memory: the fp32 slot written below (EPI 1: the only one;
+        // EPI 2: the one whose residual is being consumed was free already, the OTHER one receives the next residual after the
+        // barrier) and the single bf16 slot
+        if (lead_warp && elect_one()) bulk_wait_read_all();
+        named_bar_sync(1 + half, 128);
+        if (EPI == 2) {
+          // all threads have left the previous slice (incl. its column-statistics reads): the other slot may be refilled
+          if (sl + 2 < nsl && lead_warp && elect_one()) issue_res(sl + 2, g + 1);
+          mbar_wait(res_full(g & 1u), (g >> 1) & 1u);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 rv = lds128(f_row + (((uint32_t)j ^ sw64) << 4));
-              f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
-            }
+          for (uint32_t j = 0; j < NCF; ++j) {
+            const float4 rv = lds128(f_row + ((j ^ swf) << 4));
+            f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
           }
-          if (p.stats_out != nullptr && valid) {
+        }
+        if (p.stats_out != nullptr && valid) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { st_sum += f[i]; st_sq += f[i] * f[i]; }
-          }
-          if (p.colstats != nullptr && !valid) {                // rows outside the output must not count in the column sums
+          for (int i = 0; i < SLW; ++i) { st_sum += f[i]; st_sq += f[i] * f[i]; }
+        }
+        if (p.colstats != nullptr && !valid) {                // rows outside the output must not count in the column sums
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = 0.f;
-          }
+          for (int i = 0; i < SLW; ++i) f[i] = 0.f;
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) sts128(f_row + (((uint32_t)j ^ sw64) << 4), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          if (p.out2 != nullptr) {
+        for (uint32_t j = 0; j < NCF; ++j) sts128(f_row + ((j ^ swf) << 4), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        if (p.out2 != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              sts128u(h_row + (((uint32_t)j ^ sw32) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                      pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          }
-          fence_proxy_async();
-          named_bar_sync(1 + half, 128);
-          if (elected) {
-            tma_store_4d(&maps.o, f_row - row * 64, n, x0, y0, b0);
-            if (p.out2 != nullptr) tma_store_4d(&maps.o2, h_row - row * 32, n, x0, y0, b0);
-            bulk_commit_group();
-          }
-          if (p.colstats != nullptr) {
-            // GroupNorm statistics for free: column sums of the staged slice over the tile's 128 rows.  Warp wq of the
-            // half-group owns columns 4 wq .. 4 wq + 3 (one 16-byte chunk); lane = (row phase 0..7, column 0..3) walks rows
-            // phase + 8 i, which the SWIZZLE_64B layout spreads over all 32 banks; three shuffles fold the 8 phases.
-            const uint32_t wq = (uint32_t)(warp - 2) & 3u, cc = (uint32_t)lane & 3u, r0 = (uint32_t)lane >> 2;
-            const uint32_t fb = f_row - row * 64;
+          for (uint32_t j = 0; j < NCH; ++j)
+            sts128u(h_row + ((j ^ swh) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + half, 128);
+        if (lead_warp && elect_one()) {
+          tma_store_4d(&maps.o, f_slot, n, x0, y0, b0);
+          if (p.out2 != nullptr) tma_store_4d(&maps.o2, st_h, n, x0, y0, b0);
+          bulk_commit_group();
+        }
+        if (p.colstats != nullptr) {
+          // GroupNorm statistics for free: column sums of the staged slice over the tile's 128 rows.  Warp wq of the half-group
+          // owns NCF / 4 16-byte chunks (4 columns each); lane = (row phase 0..7, column 0..3) walks rows phase + 8 i of one
+          // chunk, which the swizzled layout spreads over all 32 banks; three shuffles fold the 8 phases.
+          const uint32_t wq = (uint32_t)(warp - 2) & 3u, cc = (uint32_t)lane & 3u, r0 = (uint32_t)lane >> 2;
+#pragma unroll
+          for (uint32_t ch = 0; ch < NCF / 4; ++ch) {
+            const uint32_t chunk = (NCF / 4) * wq + ch;
             float cs = 0.f, cq = 0.f;
 #pragma unroll
             for (uint32_t i = 0; i < 16; ++i) {
-              const uint32_t r = r0 + 8u * i;
-              const float v = lds32(fb + r * 64u + ((wq ^ ((r >> 1) & 3u)) << 4) + cc * 4u);
+              const uint32_t rr = r0 + 8u * i;
+              const uint32_t sw = (SLW == 32) ? (rr & 7u) : ((rr >> 1) & 3u);
+              const float v = lds32(f_slot + rr * (uint32_t)(SLW * 4) + ((chunk ^ sw) << 4) + cc * 4u);
               cs += v;
               cq += v * v;
             }
@@ -839,10 +855,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               cq += __shfl_xor_sync(0xffffffffu, cq, o);
             }
             if (lane < 4 && m_tile < p.m_tiles)
-              *reinterpret_cast<float2*>(p.colstats + ((long long)m_tile * p.N + n + 4 * (int)wq + lane) * 2) = make_float2(cs, cq);
+              *reinterpret_cast<float2*>(p.colstats + ((long long)m_tile * p.N + n + 4 * (int)chunk + lane) * 2) = make_float2(cs, cq);
           }
-          ++g;
         }
+        ++g;
       }
       if (p.stats_out != nullptr && valid) {
         float* sp = p.stats_out + (pix * p.n_tiles + ti.n_tile) * 8;
@@ -851,7 +867,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
       TRACE_ADD(tr_busy, tb0);
     }
-    if (elected) bulk_wait_read_all();                          // staging memory must outlive the last store's read
+    if (lead_warp && elect_one()) bulk_wait_read_all();         // staging memory must outlive the last store's read
     if (warp == 2) { TRACE_PUT(6, tr_wait_tfull); TRACE_PUT(7, tr_busy); }
 #ifdef IA2P_TC_TRACE
     if (warp == 2) TRACE_PUT(11, gtime_ns());                          // this CTA's epilogue is done
@@ -1401,22 +1417,25 @@ static int dispatch_bn(const TcMaps& maps, TcParams& p, cudaStream_t st) {
 
 static int dispatch_tc(TcMaps& maps, TcParams& p, int bn, cudaStream_t st) {
   if (tma_epilogue(p)) {
-    // output maps: same pixel-box geometry as the A operand, 16 columns wide
+    // output maps: same pixel-box geometry as the A operand, 32 columns wide (fp32: 128-byte rows, bf16 copy: 64-byte rows)
     const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TB = 128 >> (p.tw_log2 + p.th_log2);
-    const uint32_t box[4] = {16, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+    const bool wide = tma_residual(p);                  // EPI 2: 32-column slices, EPI 1: 16 (TcCfg::SLW)
+    const uint32_t box[4] = {wide ? 32u : 16u, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+    const CUtensorMapSwizzle sw_f = wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle sw_h = wide ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     const uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
     const uint64_t str[4] = {1, (uint64_t)(p.ost_x ? p.ost_x : p.ldo), (uint64_t)(p.ost_y ? p.ost_y : p.ldo * p.Wo),
                              (uint64_t)(p.ost_b ? p.ost_b : p.ldo * p.Wo * p.Ho)};
-    if (int e = make_map(&maps.o, p.out, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    if (int e = make_map(&maps.o, p.out, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sw_f)) return e;
     maps.o2 = maps.o;
     if (p.out2 != nullptr) {
       const uint64_t str2[4] = {1, (uint64_t)p.ldo2, (uint64_t)p.ldo2 * p.Wo, (uint64_t)p.ldo2 * p.Wo * p.Ho};
-      if (int e = make_map(&maps.o2, p.out2, 4, dims, str2, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
+      if (int e = make_map(&maps.o2, p.out2, 4, dims, str2, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, sw_h)) return e;
     }
     maps.r = maps.o;
     if (tma_residual(p)) {
       const uint64_t strr[4] = {1, (uint64_t)p.ldr, (uint64_t)p.ldr * p.Wo, (uint64_t)p.ldr * p.Wo * p.Ho};
-      if (int e = make_map(&maps.r, p.residual, 4, dims, strr, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+      if (int e = make_map(&maps.r, p.residual, 4, dims, strr, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sw_f)) return e;
     }
   } else if (tma_epilogue_bf16(p)) {
     // bf16 output maps: the A operand's pixel-box geometry, 64 columns (SWIZZLE_128B) and 32 columns (remainder slice, SWIZZLE_64B)
