@@ -253,11 +253,18 @@ class B200UNet(nn.Module):
     def from_module(cls, unet, device=None):
         """Build from a diffusers ``UNet2DConditionModel`` (or the oracle): copies config, weights and processors."""
         device = device or getattr(unet, "device", "cuda")
-        new = cls(unet.config, device=device)
+        # Build where the source lives and move ONCE: for a CPU source (a checkpoint just loaded, the oracle) construction,
+        # parameter initialisation and the state-dict copy stay on the host and the device only sees memcpys -- no stream of
+        # initialisation kernels in front of the first real launch (the driver's launch record of smoke() starts there).
+        src_dev = next(iter(unet.parameters())).device if hasattr(unet, "parameters") else torch.device(device)
+        new = cls(unet.config, device=src_dev)
         # processors first: nn.Module processors are registered sub-modules, so their weights appear in state_dict()
         # under "...attn2.processor.to_k_ip.weight" on both sides (same as diffusers)
         new.set_attn_processor({k: new._adopt_processor(v, k) for k, v in unet.attn_processors.items()})
         new.load_state_dict(unet.state_dict())
+        if torch.device(device) != src_dev:
+            new.to(device)
+            new.invalidate()
         return new
 
     def _adopt_processor(self, proc, name):

@@ -35,6 +35,26 @@ def test_shard_indices_cover_everything_once():
             assert allidx == list(range(n))
             sizes = [len(shard_indices(n, r, w)) for r in range(w)]
             assert max(sizes) - min(sizes) <= 1
+            for block in (2, 4):
+                per_rank = [shard_indices(n, r, w, block) for r in range(w)]
+                assert sorted(i for idx in per_rank for i in idx) == list(range(n))
+                # whole batches: every chunk of `block` local requests is one aligned run of consecutive global indices
+                for idx in per_rank:
+                    for c in range(0, len(idx), block):
+                        chunk = idx[c:c + block]
+                        assert chunk[0] % block == 0 and chunk == list(range(chunk[0], chunk[0] + len(chunk)))
+
+
+def test_batches_are_the_same_for_every_gpu_count():
+    """bit-identical output for 1..8 GPUs needs every request to run in the same batch, in the same slot, for every world size"""
+    n, block = 37, 4
+    ref = {tuple(range(b, min(b + block, n))) for b in range(0, n, block)}
+    for w in (1, 2, 4, 8):
+        got = set()
+        for r in range(w):
+            idx = shard_indices(n, r, w, block)
+            got |= {tuple(idx[c:c + block]) for c in range(0, len(idx), block)}
+        assert got == ref
 
 
 def test_two_rank_result_equals_single_process():

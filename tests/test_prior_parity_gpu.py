@@ -32,15 +32,53 @@ def test_prior_matches_reference_golden(case, graph):
     assert c >= 0.999
 
 
-def test_prior_batched_8():
+class _RandnReplay:
+    """Both paths draw their noise through torch.randn (initial x, then one draw per ancestral step, prior/model.py:580,597-599 and
+    [3P] DDPMScheduler.step); the batched B200 call draws (bs, 1, E) tensors, the per-sample oracle (1, 1, E).  Replaying ONE
+    pre-drawn sequence -- whole tensors for the batch, row i for sample i -- gives every sample identical noise on both sides."""
+
+    def __init__(self, draws, row=None):
+        self.draws, self.row, self.i, self.real = draws, row, 0, torch.randn
+
+    def __call__(self, *size, **kw):
+        size = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
+        if len(size) == 3 and size[1:] == (1, 1024):
+            d = self.draws[self.i]
+            self.i += 1
+            d = d if self.row is None else d[self.row:self.row + 1]
+            assert d.shape[0] == size[0]
+            return d.clone().to(kw.get("device", "cpu"))
+        return self.real(*size, **kw)
+
+    def __enter__(self):
+        torch.randn = self
+        return self
+
+    def __exit__(self, *a):
+        torch.randn = self.real
+
+
+@pytest.mark.parametrize("no_diffusion", [True, False], ids=["production_call", "25_step_diffusion"])
+def test_prior_batched_8_rows_match_the_per_sample_oracle(no_diffusion):
+    """C4 runs the prior at batch 8 per GPU; the reference cannot batch (prior/model.py:569,580).  Every row of the batched CUDA
+    call must equal the fp32 oracle run on that sample alone with the same noise: cosine >= 0.999 (north-star gate) per row."""
     o, b = build(24, device="cuda", graph=True)
     clip_hidden = G.prior_inputs("l24_nodiff")[1]
     b.set_clip_hidden(clip_hidden)
     srcs = torch.stack([G.prior_inputs(f"b{i}")[0][0] for i in range(8)])
-    torch.manual_seed(11)
-    yb, _ = b.generate_diffusion(3, 0, srcs, device="cpu", dtype=torch.float32, num_inference_steps=25, guidance_scale=10, score=6.5)
+    g = torch.Generator().manual_seed(11)
+    draws = [torch.randn(8, 1, 1024, generator=g) for _ in range(32)]
+    kw = dict(no_diffusion=no_diffusion, num_inference_steps=25, guidance_scale=10, score=6.5)
+    with _RandnReplay(draws):
+        yb, _ = b.generate_diffusion(3, 0, srcs, device="cpu", dtype=torch.float32, **kw)
     assert yb.shape == (8, 1, 1024) and torch.isfinite(yb).all()
-    # per-sample runs with the same per-row noise must agree with the batched rows
-    torch.manual_seed(11)
-    y0, _ = b.generate_diffusion(3, 0, srcs, device="cpu", dtype=torch.float32, num_inference_steps=25, guidance_scale=10, score=6.5)
-    assert torch.equal(yb, y0)       # bit-reproducible
+    worst = 1.0
+    for i in range(8):
+        with _RandnReplay(draws, row=i):
+            yo, _ = o.generate_diffusion(3, 0, srcs[i], clip_hidden, **kw)
+        worst = min(worst, cos(yb[i], yo))
+    print(f"prior batch 8 (no_diffusion={no_diffusion}): worst row cosine vs the per-sample oracle {worst:.6f}")
+    assert worst >= 0.999
+    with _RandnReplay(draws):                             # and the batched call is bit-reproducible
+        y0, _ = b.generate_diffusion(3, 0, srcs, device="cpu", dtype=torch.float32, **kw)
+    assert torch.equal(yb, y0)
