@@ -42,6 +42,8 @@ WORKLOADS = {
     "c4": dict(L=128, B=8, prior=True, name="instruction-edit: prior + 1024^2 UNet sampling, batch 8 per GPU"),
     "b1": dict(L=128, B=1, prior=False, name="single interactive request: SDXL-class UNet 1024^2 50-step DDIM CFG, batch 1"),
     "c1": dict(L=None, B=1, prior=True, name="instructany2pix/prior embedding-prior sampling (GPT-2-medium trunk, 25 DDPM steps, CFG), 1 sample"),
+    # the refinement pass every request ends with (pipeline.py:128-131, :358-361: piperf(image=..., strength=0.5))
+    "rf": dict(L=128, B=4, prior=False, refiner=True, name="SDXL-refiner UNet 1024^2 img2img: strength 0.5 of a 50-step Euler schedule (25 CFG steps), batch 4"),
 }
 PRIOR_STEPS = 25
 
@@ -101,21 +103,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ model + inputs
-def build_models(dev, want_prior):
+def build_models(dev, want_prior, refiner=False):
     from instructany2pix_b200.attention_processor import B200IPAttnProcessor
-    from instructany2pix_b200.unet import B200UNet
+    from instructany2pix_b200.unet import REFINER_CONFIG, B200UNet
 
     g = torch.Generator(device=dev)
     g.manual_seed(0)
-    unet = B200UNet(device=dev)                                  # SDXL-base config: 2 567 463 684 parameters
-    procs = {}
-    for name, p in unet.attn_processors.items():
-        if name.endswith("attn2.processor"):
-            hs = dict(unet.named_modules())[name[: -len(".processor")]].to_q.weight.shape[0]
-            procs[name] = B200IPAttnProcessor(hs, unet.config.cross_attention_dim, scale=1.0, num_tokens=4, device=dev)
-        else:
-            procs[name] = p
-    unet.set_attn_processor(procs)                               # +340 787 200 IP-adapter parameters
+    if refiner:
+        unet = B200UNet(device=dev, **REFINER_CONFIG)            # SDXL-refiner config: 2 259 526 660 parameters, text-only cross-attention
+    else:
+        unet = B200UNet(device=dev)                              # SDXL-base config: 2 567 463 684 parameters
+        procs = {}
+        for name, p in unet.attn_processors.items():
+            if name.endswith("attn2.processor"):
+                hs = dict(unet.named_modules())[name[: -len(".processor")]].to_q.weight.shape[0]
+                procs[name] = B200IPAttnProcessor(hs, unet.config.cross_attention_dim, scale=1.0, num_tokens=4, device=dev)
+            else:
+                procs[name] = p
+        unet.set_attn_processor(procs)                           # +340 787 200 IP-adapter parameters
     for name, p in unet.named_parameters():                      # PyTorch-default-scale random init, on the device
         if p.ndim >= 2:
             fan_in = p[0].numel()
@@ -140,12 +145,13 @@ def build_models(dev, want_prior):
     return unet, prior
 
 
-def build_vae(dev):
-    """SDXL AutoencoderKL decoder (random init of the named architecture) for the end-to-end leg: latents -> images."""
+def build_vae(dev, with_encoder=False):
+    """SDXL AutoencoderKL decoder (random init of the named architecture) for the end-to-end leg: latents -> images
+    (+ the encoder for the refiner workload: image -> latents)."""
     from instructany2pix_b200.vae import B200VAE
     g = torch.Generator(device=dev)
     g.manual_seed(1)
-    vae = B200VAE(device=dev, with_encoder=False)
+    vae = B200VAE(device=dev, with_encoder=with_encoder)
     for name, p in vae.named_parameters():
         if p.ndim >= 2:
             fan_in = p[0].numel()
@@ -158,19 +164,26 @@ def build_vae(dev):
     return vae
 
 
+REFINER = False          # set by main() for the "rf" workload: text context 1280 wide, five micro-conditioning ids, an input image
+
+
 def request_inputs(i, L):
     """Synthetic conditioning of ONE request, a function of its GLOBAL index only: [negative ; positive] prompt tokens,
-    pooled embeddings, micro-conditioning ids, start noise, LLM image embedding."""
+    pooled embeddings, micro-conditioning ids, start noise, LLM image embedding (refiner: the image to refine instead)."""
     g = torch.Generator()
     g.manual_seed(1000 + i)
-    ctx = torch.randn(2, 77, 2048, generator=g)
+    ctx = torch.randn(2, 77, 1280 if REFINER else 2048, generator=g)
     pooled = torch.randn(2, 1280, generator=g)
     H = float(L * 8)
-    tid = torch.tensor([[H, H, 0.0, 0.0, H, H]]).repeat(2, 1)
+    tid = torch.tensor([[H, H, 0.0, 0.0, 6.0]] if REFINER else [[H, H, 0.0, 0.0, H, H]]).repeat(2, 1)   # refiner: (size, crop, aesthetic score)
+    tid[0, -1] = 2.5 if REFINER else tid[0, -1]                 # negative_aesthetic_score
     lat = torch.randn(4, L, L, generator=g)
     e = torch.randn(1, 1024, generator=g)
     e = e / e.norm(dim=-1, keepdim=True) * 100.0
-    return dict(ctx=ctx, pooled=pooled, tid=tid, lat=lat, llm=e)
+    out = dict(ctx=ctx, pooled=pooled, tid=tid, lat=lat, llm=e)
+    if REFINER:
+        out["image"] = torch.rand(3, 8 * L, 8 * L, generator=g) * 2 - 1
+    return out
 
 
 def host_batch(indices, L):
@@ -179,9 +192,12 @@ def host_batch(indices, L):
     rs = [request_inputs(i, L) for i in indices]
     pin = lambda t: t.contiguous().pin_memory() if torch.cuda.is_available() else t.contiguous()
     half = lambda k, j: torch.stack([r[k][j] for r in rs])
-    return dict(ctx=pin(torch.cat([half("ctx", 0), half("ctx", 1)])), pooled=pin(torch.cat([half("pooled", 0), half("pooled", 1)])),
-                tid=pin(torch.cat([half("tid", 0), half("tid", 1)])), lat=pin(torch.stack([r["lat"] for r in rs])),
-                llm=pin(torch.stack([r["llm"] for r in rs])))
+    out = dict(ctx=pin(torch.cat([half("ctx", 0), half("ctx", 1)])), pooled=pin(torch.cat([half("pooled", 0), half("pooled", 1)])),
+               tid=pin(torch.cat([half("tid", 0), half("tid", 1)])), lat=pin(torch.stack([r["lat"] for r in rs])),
+               llm=pin(torch.stack([r["llm"] for r in rs])))
+    if REFINER:
+        out["image"] = pin(torch.stack([r["image"] for r in rs]))
+    return out
 
 
 def host_inputs(B, L, seed):
@@ -190,7 +206,12 @@ def host_inputs(B, L, seed):
 
 
 def run_trajectory(hot, dev_in, steps):
-    """one request batch: (prior ->) LLM embedding -> ImageProj -> 4 IP tokens appended to the text tokens -> CFG sampling"""
+    """one request batch: (prior ->) LLM embedding -> ImageProj -> 4 IP tokens appended to the text tokens -> CFG sampling;
+    refiner: [image -> VAE encode ->] add_noise at strength 0.5 -> the last half of the Euler schedule, text-only CFG"""
+    if REFINER:
+        init = dev_in["init"] if "init" in dev_in else hot.vae.encode(dev_in["image"], sample=False)
+        return hot.sampler.generate(dev_in["lat"], dev_in["ctx"], dict(text_embeds=dev_in["pooled"], time_ids=dev_in["tid"]),
+                                    num_inference_steps=steps, guidance_scale=5.0, init_latents=init, strength=0.5)
     y = None
     if hot.prior is not None:
         y = hot.prior.generate_diffusion(3, 0, dev_in["llm"], device=dev_in["llm"].device, dtype=torch.float32,
@@ -297,6 +318,8 @@ def make_config(wl, world, NS, graph=True):
 
 
 def metric_name(wl):
+    if wl.get("refiner"):
+        return "images/sec 1024^2 refiner img2img (25 of 50 Euler steps, CFG)"
     if wl["L"] is None:
         return "prior samples/sec (25-step DDPM CFG embedding-prior sampling)"
     return "images/sec 1024^2 50-step DDIM CFG" if wl["L"] == 128 else "images/sec 512^2 50-step DDIM CFG"
@@ -560,16 +583,23 @@ def main():
     import hashlib
 
     from instructany2pix_b200 import ops, parallel
+    global REFINER
+    REFINER = bool(wl.get("refiner"))
     L, B, NS = wl["L"], wl["B"], args.num_inference_steps
-    unet, prior = build_models(dev, wl["prior"])
-    vae = build_vae(dev)
+    unet, prior = build_models(dev, wl["prior"], refiner=REFINER)
+    vae = build_vae(dev, with_encoder=REFINER)
     from instructany2pix_b200.hotpath import B200HotPath
     from instructany2pix_b200.image_proj import B200ImageProj
+    from instructany2pix_b200.scheduler import B200EulerDiscreteScheduler
     proj = B200ImageProj(device=dev)                             # Linear(1024 -> 4 x 2048) + LayerNorm(2048), PyTorch-default init
-    hot = B200HotPath(unet, vae, prior=prior, use_cuda_graph=not args.no_graph, image_proj=proj)
+    hot = B200HotPath(unet, vae, scheduler=B200EulerDiscreteScheduler() if REFINER else None, prior=prior,
+                      use_cuda_graph=not args.no_graph, image_proj=proj)
     sampler = hot.sampler
+    n_unet_steps = int(NS * 0.5) if REFINER else NS              # img2img at strength 0.5 runs the last half of the schedule
     host = host_batch(list(range(rank * B, rank * B + B)), L)    # device-resident leg: this rank's first request batch
     dev_in = {k: v.to(dev) for k, v in host.items()}
+    if REFINER:                                                  # device-resident leg: the image is already encoded
+        dev_in["init"] = vae.encode(dev_in.pop("image"), sample=False)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -638,13 +668,14 @@ def main():
     ms_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
     e2e_value = n_items / (ms_e2e / 1e3)
-    unet_step_ms = ms_step / NS
-    step_flops = 2 * B * F_UNET[L]
-    whole_frac = step_flops / (unet_step_ms * 1e-3) / (pk["sustained"] * 1e12)
+    unet_step_ms = ms_step / n_unet_steps
     # launches: graph replays re-issue the captured kernels
-    by = profile_dominant_kernel(unet, sampler, dev_in, B, hot.ip_context(dev_in["ctx"], dev_in["llm"]))
+    by = profile_dominant_kernel(unet, sampler, dev_in, B, dev_in["ctx"] if REFINER else hot.ip_context(dev_in["ctx"], dev_in["llm"]))
+    # FLOPs of one CFG step: the analytic count of the SDXL-base forward, else what the ops of one forward count
+    step_flops = 2 * B * F_UNET[L] if not REFINER else sum(d["flops"] for d in by.values())
+    whole_frac = step_flops / (unet_step_ms * 1e-3) / (pk["sustained"] * 1e12)
     n_forward_kernels = sum(d["n"] * ops._KERNELS_PER_CALL.get(k, 1) for k, d in by.items())
-    gpu_launches = launches_eager + (0 if args.no_graph else args.steps * NS * n_forward_kernels)
+    gpu_launches = launches_eager + (0 if args.no_graph else args.steps * n_unet_steps * n_forward_kernels)
     tc = dict(ms=0.0, flops=0.0, n=0, bytes=0.0)
     for k in ("ia2p_gemm_bf16", "ia2p_gemm_ln_bf16", "ia2p_conv3x3_nhwc_bf16", "ia2p_conv_up2x_nhwc_bf16"):
         if k in by:
@@ -668,12 +699,16 @@ def main():
                                  "50-step trajectory, VAE decode to fp32 images; then ordered gather of every rank's images on rank 0 (NCCL) and D2H",
                         requests=n_items, first_batch_sha256=sha, vae_decode_ms=ms_decode),
                gpu_launches=int(gpu_launches), roofline=roof)
-    if world == 1 and not args.no_eager_baseline:
+    if REFINER:
+        out["config"].update(num_inference_steps=NS, strength=0.5, unet_steps=n_unet_steps, guidance_scale=5.0, scheduler="EulerDiscrete")
+        out["e2e"]["includes"] = ("per request batch: H2D of the image to refine + text conditioning + noise, VAE encode, add_noise, 25 CFG steps of the "
+                                  "refiner UNet, VAE decode to fp32 images; then ordered gather on rank 0 and D2H")
+    if world == 1 and not args.no_eager_baseline and not REFINER:
         t = eager_gpu_step_ms(dev, B, L)
         out["gpu_eager_baseline"] = dict(unet_step_ms=t, value=B / (NS * t * 1e-3), unit="images/sec", speedup_of_this_build=t / unet_step_ms,
                                          what="PyTorch eager bf16 (the oracle's restated UNet + processors on the same GPU: cuDNN / cuBLAS / SDPA), "
                                               "one CFG UNet step incl. CFG + DDIM arithmetic, x50 for images/sec")
-    if not args.no_cpu_baseline and world == 1:                 # contract: rank 0 at N = 1 only
+    if not args.no_cpu_baseline and world == 1 and not REFINER:  # contract: rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         cpu_unet_step_seconds(L, cores)                          # warm-up: allocator, thread pool, oneDNN primitives
         t = cpu_unet_step_seconds(L, cores)

@@ -6,36 +6,94 @@
 
 namespace ia2p {
 
+// ---------------------------------------------------------------- 128-bit accesses for the one-pass elementwise kernels
+// Eight consecutive elements per thread and iteration: two LDG.128 / STG.128 for fp32, one for bf16 / fp16 (north_star: "vectorised
+// 128-bit coalesced epilogues").  Callers guarantee 16-byte alignment and a multiple-of-8 element count (else the scalar kernels run).
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 t;
+  t = unpack_bf16x2(a.x); v[0] = t.x; v[1] = t.y; t = unpack_bf16x2(a.y); v[2] = t.x; v[3] = t.y;
+  t = unpack_bf16x2(a.z); v[4] = t.x; v[5] = t.y; t = unpack_bf16x2(a.w); v[6] = t.x; v[7] = t.y;
+}
+template <> __device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+template <> __device__ __forceinline__ void store8<__half>(__half* p, const float (&v)[8]) {
+  uint4 a;
+  __half2* h = reinterpret_cast<__half2*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = a;
+}
+
 // ---------------------------------------------------------------- CFG + DDIM (one pass over the latents)
-template <typename TE, typename TX, typename TI>
+// VEC = true: 8 elements per thread and iteration through 128-bit loads / stores; VEC = false: scalar fallback for unaligned or
+// ragged sizes.  total = batch * n; eps_u at [i], eps_c at [total + i].
+template <typename TE, typename TX, typename TI, bool VEC>
 __global__ void cfg_ddim_kernel(const TE* __restrict__ eps2, const TX* __restrict__ x, TX* __restrict__ x_out,
                                 TI* __restrict__ x_in2, long long total, float g, float cx, float ce) {
   pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
   pdl_wait();
-  // total = batch * n; eps_u at [i], eps_c at [total + i]
-  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total;
-       i += (long long)gridDim.x * blockDim.x * 4) {
+  constexpr int W = VEC ? 8 : 1;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * W; i < total; i += (long long)gridDim.x * blockDim.x * W) {
+    if constexpr (VEC) {
+      float eu[8], ec[8], xv[8], v[8];
+      load8(eps2 + i, eu);
+      load8(eps2 + total + i, ec);
+      load8(x + i, xv);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float eu = load_as_float(eps2 + i + j), ec = load_as_float(eps2 + total + i + j);
-      const float e = eu + g * (ec - eu);
-      const float v = cx * load_as_float(x + i + j) + ce * e;
-      store_from_float(x_out + i + j, v);
+      for (int j = 0; j < 8; ++j) v[j] = cx * xv[j] + ce * (eu[j] + g * (ec[j] - eu[j]));
+      store8(x_out + i, v);
       if (x_in2 != nullptr) {
-        store_from_float(x_in2 + i + j, v);
-        store_from_float(x_in2 + total + i + j, v);
+        store8(x_in2 + i, v);
+        store8(x_in2 + total + i, v);
+      }
+    } else {
+      const float eu = load_as_float(eps2 + i), ec = load_as_float(eps2 + total + i);
+      const float v = cx * load_as_float(x + i) + ce * (eu + g * (ec - eu));
+      store_from_float(x_out + i, v);
+      if (x_in2 != nullptr) {
+        store_from_float(x_in2 + i, v);
+        store_from_float(x_in2 + total + i, v);
       }
     }
   }
 }
 
-template <typename TE, typename TX>
+template <typename TE, typename TX, bool VEC>
 __global__ void axpby_kernel(const TE* __restrict__ eps, const TX* __restrict__ x, TX* __restrict__ out, long long n,
                              float cx, float ce) {
   pdl_launch_dependents();   // programmatic dependent launch: see common.cuh
   pdl_wait();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    store_from_float(out + i, cx * load_as_float(x + i) + ce * load_as_float(eps + i));
+  constexpr int W = VEC ? 8 : 1;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * W; i < n; i += (long long)gridDim.x * blockDim.x * W) {
+    if constexpr (VEC) {
+      float e[8], xv[8], v[8];
+      load8(eps + i, e);
+      load8(x + i, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = cx * xv[j] + ce * e[j];
+      store8(out + i, v);
+    } else {
+      store_from_float(out + i, cx * load_as_float(x + i) + ce * load_as_float(eps + i));
+    }
+  }
 }
 
 __global__ void prior_step_kernel(const float* __restrict__ x0_pair, const float* __restrict__ x,
@@ -436,15 +494,24 @@ extern "C" int ia2p_cfg_ddim_step(const void* eps2, int eps_dtype, const void* x
                                   float c_e, void* stream) {
   if (int e = check_device()) return e;
   IA2P_REQUIRE(eps2 && x && x_out && batch > 0 && n > 0, IA2P_E_ARG, "cfg_ddim_step: null pointer or empty shape");
-  IA2P_REQUIRE(n % 4 == 0, IA2P_E_SHAPE, "cfg_ddim_step: n=%lld must be a multiple of 4", (long long)n);
   const long long total = batch * n;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = grid_for(total / 4, 256);
   if (x_in_next2 == nullptr) xin_dtype = x_dtype;
-  DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(xin_dtype, TI,
-      (launch_pdl(cfg_ddim_kernel<TE, TX, TI>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps2), static_cast<const TX*>(x),
-                                                         static_cast<TX*>(x_out), static_cast<TI*>(x_in_next2), total,
-                                                         g, c_x, c_e)))));
+  auto esz = [](int dt) { return dt == IA2P_F32 ? 4ll : 2ll; };
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  // 128-bit path: every 8-element group of every array starts on a 16-byte boundary (the second halves start at `total`)
+  const bool vec = total % 8 == 0 && al16(eps2) && al16(x) && al16(x_out) && (x_in_next2 == nullptr || al16(x_in_next2)) &&
+                   (total * esz(eps_dtype)) % 16 == 0 && (total * esz(xin_dtype)) % 16 == 0;
+  const int grid = grid_for(vec ? total / 8 : total, 256);
+  if (vec) {
+    DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(xin_dtype, TI,
+        (launch_pdl(cfg_ddim_kernel<TE, TX, TI, true>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps2), static_cast<const TX*>(x),
+                    static_cast<TX*>(x_out), static_cast<TI*>(x_in_next2), total, g, c_x, c_e)))));
+  } else {
+    DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(xin_dtype, TI,
+        (launch_pdl(cfg_ddim_kernel<TE, TX, TI, false>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps2), static_cast<const TX*>(x),
+                    static_cast<TX*>(x_out), static_cast<TI*>(x_in_next2), total, g, c_x, c_e)))));
+  }
   IA2P_LAUNCH_CHECK();
   return 0;
 }
@@ -454,10 +521,18 @@ extern "C" int ia2p_axpby(const void* eps, int eps_dtype, const void* x, void* x
   if (int e = check_device()) return e;
   IA2P_REQUIRE(eps && x && x_out && n > 0, IA2P_E_ARG, "axpby: null pointer or empty shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = grid_for(n, 256);
-  DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX,
-      (launch_pdl(axpby_kernel<TE, TX>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps), static_cast<const TX*>(x),
-                                                  static_cast<TX*>(x_out), n, c_x, c_e))));
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = n % 8 == 0 && al16(eps) && al16(x) && al16(x_out);
+  const int grid = grid_for(vec ? n / 8 : n, 256);
+  if (vec) {
+    DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX,
+        (launch_pdl(axpby_kernel<TE, TX, true>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps), static_cast<const TX*>(x),
+                    static_cast<TX*>(x_out), n, c_x, c_e))));
+  } else {
+    DISPATCH_DTYPE(eps_dtype, TE, DISPATCH_DTYPE(x_dtype, TX,
+        (launch_pdl(axpby_kernel<TE, TX, false>, dim3(grid), dim3(256), 0, st, static_cast<const TE*>(eps), static_cast<const TX*>(x),
+                    static_cast<TX*>(x_out), n, c_x, c_e))));
+  }
   IA2P_LAUNCH_CHECK();
   return 0;
 }
@@ -539,7 +614,8 @@ extern "C" int ia2p_conv_in_nchw(const void* x, int x_dtype, int64_t in_batch, i
   if (int e = check_device()) return e;
   IA2P_REQUIRE(x && w && out && B > 0 && in_batch > 0 && H > 0 && W > 0, IA2P_E_ARG, "conv_in: bad arguments");
   IA2P_REQUIRE(out_dtype == IA2P_BF16 || out_dtype == IA2P_F32, IA2P_E_ARG, "conv_in: out_dtype must be bf16 or f32");
-  IA2P_REQUIRE(Cin >= 1 && Cin <= 8 && Cout % 8 == 0 && Cout <= 640, IA2P_E_SHAPE, "conv_in: Cin<=8, Cout%%8==0, Cout<=640 required");
+  // Cin = 4: latents; 8 / 9: inpainting UNets (latents + mask + masked-image latents, [3P] StableDiffusionXLInpaintPipeline)
+  IA2P_REQUIRE(Cin >= 1 && Cin <= 16 && Cout % 8 == 0 && Cout <= 640, IA2P_E_SHAPE, "conv_in: Cin<=16, Cout%%8==0, Cout<=640 required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long npix = B * H * W;
   const size_t smem = (size_t)Cin * 9 * (Cout + kConvInTile) * sizeof(float);

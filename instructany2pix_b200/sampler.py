@@ -67,7 +67,8 @@ class B200Sampler:
         n_ip, ip_scale = unet._ip_state()
         key = (kind, tuple(latents.shape), unet_batch, tuple(kv[0].shape), None if kv[1] is None else tuple(kv[1].shape),
                kv[2], kv[3], ip_scale, unet._proc_version, id(unet._packed))
-        ent = self._static(key, latents.shape, unet_batch, kv, table.shape[-1], dev)
+        cin = int(getattr(unet.config, "in_channels", 4))      # 9: inpainting UNet (latents + mask + masked-image latents)
+        ent = self._static(key, (latents.shape[0], cin) + tuple(latents.shape[2:]), unet_batch, kv, table.shape[-1], dev)
         ent["kv_t"].copy_(kv[0])
         if kv[1] is not None:
             ent["kv_i"].copy_(kv[1])
@@ -95,7 +96,7 @@ class B200Sampler:
     # ------------------------------------------------------------------ generation (CFG, DDIM eta=0)
     @torch.no_grad()
     def generate(self, latents, ctx, added_cond_kwargs, num_inference_steps=50, guidance_scale=10.0, trace=None,
-                 teacher=None, init_latents=None, strength=1.0, inpaint_mask=None):
+                 teacher=None, init_latents=None, strength=1.0, inpaint_mask=None, masked_image_latents=None):
         """latents: (B,4,L,L) initial noise; ctx: (2B,S,D) = cat([negative, positive]) incl. IP tokens
         (ip_adapter.py:341-342, custom_pipelines.py:296-302); added_cond_kwargs: text_embeds (2B,P), time_ids (2B,6).
         Returns final latents (B,4,L,L) fp32 on the device.
@@ -103,7 +104,13 @@ class B200Sampler:
         img2img / refiner (pipeline.py:358-361, [3P] StableDiffusionXLImg2ImgPipeline): ``init_latents`` (the encoded image) and
         ``strength`` < 1 -> only the last int(N * strength) steps run, starting from ``add_noise(init_latents, latents, t_start)``.
         Inpainting (gdino/lib.py:85-102, [3P] StableDiffusionXLInpaintPipeline with a 4-channel UNet): additionally
-        ``inpaint_mask`` (B,1,L,L), 1 = repaint: after every step the kept region is reset to the re-noised original."""
+        ``inpaint_mask`` (B,1,L,L), 1 = repaint: after every step the kept region is reset to the re-noised original.
+        9-channel inpainting UNet (``unet.config.in_channels == 9``, the released SDXL-inpainting layout; the reference itself hands
+        the 4-channel base UNet to the pipeline, pipeline.py:132-139): the model sees ``cat([latents, mask, masked_image_latents])``
+        every step -- ``inpaint_mask`` and ``masked_image_latents`` (B,4,L,L) are required and nothing is blended."""
+        nine = int(getattr(self.unet.config, "in_channels", 4)) == 9
+        if nine and (inpaint_mask is None or masked_image_latents is None or init_latents is None):
+            raise ValueError("a 9-channel inpainting UNet needs init_latents, inpaint_mask and masked_image_latents")
         if inpaint_mask is not None and init_latents is None:
             raise ValueError("generate(inpaint_mask=...) needs init_latents (the encoded original the kept region is reset to)")
         s = self.scheduler
@@ -117,7 +124,10 @@ class B200Sampler:
             assert len(timesteps) > 0, "strength too small: no denoising step left"
         ent, table, n_text, n_ip = self._prepare("gen", latents, ctx, added_cond_kwargs, 2 * B, timesteps)
         scaled_input = hasattr(s, "input_scale")           # Euler: the UNet sees x / sqrt(sigma^2 + 1), DDIM: x itself
-        x = torch.empty_like(ent["x"]) if scaled_input else ent["x"]
+        x = torch.empty(latents.shape, device=ent["x"].device, dtype=torch.float32) if (scaled_input or nine) else ent["x"]
+        if nine:                                           # channels 4..8 of the model input are constant over the trajectory
+            ent["x"][:, 4:5].copy_(inpaint_mask.to(x.device, torch.float32))
+            ent["x"][:, 5:9].copy_(masked_image_latents.to(x.device, torch.float32))
         noise = latents.to(x.device, torch.float32)
         if init_latents is None:
             x.copy_(noise * s.init_noise_sigma)
@@ -133,14 +143,16 @@ class B200Sampler:
         for i, t in enumerate(ts_list):
             if teacher is not None:
                 x.copy_(teacher[i])
-            if scaled_input:
+            if nine:
+                ent["x"][:, :4].copy_(x * s.input_scale(t) if scaled_input else x)
+            elif scaled_input:
                 ops.axpby(x, x, s.input_scale(t), 0.0, out=ent["x"])
             ent["rb"].copy_(table[i])
             self._forward(ent, 2 * B, n_text, n_ip)
             if trace is not None:
                 trace.append(dict(t=t, x=x.clone(), eps2=ent["eps"].clone()))
             s.cfg_step(ent["eps"], t, x, guidance_scale, out=x)
-            if mask is not None:
+            if mask is not None and not nine:
                 if i + 1 < len(ts_list):
                     c_x, c_e = s.add_noise_coefficients(ts_list[i + 1])
                     ops.inpaint_blend(x, orig, noise, mask, c_x, c_e, out=x)

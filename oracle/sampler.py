@@ -26,12 +26,16 @@ def cfg_inputs(reqs, ip_tokens, ip_tokens_uncond):
 
 @torch.no_grad()
 def generate(unet, latents, ctx, added, num_inference_steps=50, guidance_scale=10.0, scheduler=None,
-             trace=None, teacher=None, init_latents=None, strength=1.0, inpaint_mask=None):
+             trace=None, teacher=None, init_latents=None, strength=1.0, inpaint_mask=None, masked_image_latents=None):
     """-> final latents (B,4,L,L).  ``trace``: list collecting (t, x_in, eps2B, x_next) per step.
     ``teacher``: optional list of per-step input latents (teacher forcing for per-step parity).
     ``init_latents`` + ``strength``: [3P] StableDiffusionXLImg2ImgPipeline semantics (get_timesteps + add_noise; the refiner call
     at pipeline.py:358-361).  ``inpaint_mask`` (B,1,L,L, 1 = repaint): [3P] StableDiffusionXLInpaintPipeline with a 4-channel UNet
-    (gdino/lib.py:85-102): after every step ``latents = (1 - m) * add_noise(init, noise, t_next) + m * latents``."""
+    (gdino/lib.py:85-102): after every step ``latents = (1 - m) * add_noise(init, noise, t_next) + m * latents``.
+    With a 9-channel inpainting UNet ([3P] same pipeline, ``num_channels_unet == 9``; not what pipeline.py:132-139 builds -- it
+    passes the base UNet -- but the configuration the released SDXL-inpainting checkpoints use) the model input is
+    ``cat([scaled latents, mask, masked_image_latents], 1)`` and NO blending happens."""
+    nine = getattr(unet.config, "in_channels", 4) == 9
     s = scheduler or DDIMSchedulerOracle()
     s.set_timesteps(num_inference_steps)
     timesteps = s.timesteps
@@ -51,11 +55,13 @@ def generate(unet, latents, ctx, added, num_inference_steps=50, guidance_scale=1
         if teacher is not None:
             x = teacher[i]
         x_in = s.scale_model_input(torch.cat([x] * 2), t)
+        if nine:
+            x_in = torch.cat([x_in, torch.cat([inpaint_mask] * 2), torch.cat([masked_image_latents] * 2)], dim=1)
         eps2 = unet(x_in, t, encoder_hidden_states=ctx, added_cond_kwargs=added, return_dict=False)[0]
         e_u, e_c = eps2.chunk(2)
         eps = e_u + guidance_scale * (e_c - e_u)
         x_next = s.step(eps, t, x, eta=0.0)[0]
-        if inpaint_mask is not None:
+        if inpaint_mask is not None and not nine:
             keep = init_latents if i + 1 >= len(timesteps) else s.add_noise(init_latents, noise, timesteps[i + 1])
             x_next = (1 - inpaint_mask) * keep + inpaint_mask * x_next
         if trace is not None:

@@ -170,3 +170,29 @@ def test_start_latent_is_per_sample(emu):
     out = s.start_latent(x, 0.7, noise=n)
     for i in range(3):
         assert torch.allclose(out[i:i + 1], s.start_latent(x[i:i + 1], 0.7, noise=n[i:i + 1]), atol=1e-6)
+
+
+def nine_channel_case(device="cpu"):
+    """TINY topology with a 9-channel conv_in: latents + mask + masked-image latents (the released SDXL-inpainting layout)"""
+    import dataclasses
+    from oracle.synth import synth_input
+    cfg = dataclasses.replace(TINY, in_channels=9)
+    o = OracleUNet(cfg).eval()
+    o.load_state_dict(synth_state_dict(o, 31))
+    b = B200UNet.from_module(o, device=device)
+    lat, ctx, added = make_inputs(TINY, B=2, L=16)
+    init = synth_input("ip9/init", (2, 4, 16, 16), seed=4) * 0.8
+    mask = (synth_input("ip9/mask", (2, 1, 16, 16), seed=5) > 0).float()
+    return o, b, lat, ctx, added, init, mask, init * (1 - mask)
+
+
+def test_nine_channel_inpainting_unet(emu):
+    o, b, lat, ctx, added, init, mask, masked = nine_channel_case()
+    assert b.conv_in.weight.shape[1] == 9 and b.config.in_channels == 9
+    kw = dict(num_inference_steps=4, guidance_scale=7.5, init_latents=init, strength=0.75, inpaint_mask=mask, masked_image_latents=masked)
+    ref = osampler.generate(o, lat, ctx, added, **kw)
+    out = B200Sampler(b, use_cuda_graph=False).generate(lat, ctx, added, **kw)
+    assert rel(out, ref) < 2e-2
+    import pytest
+    with pytest.raises(ValueError, match="9-channel"):
+        B200Sampler(b, use_cuda_graph=False).generate(lat, ctx, added, num_inference_steps=2, init_latents=init, inpaint_mask=mask)

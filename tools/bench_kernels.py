@@ -147,9 +147,39 @@ def bench_norm():
         print(f"{name}: {ms * 1e3:8.1f} us  {B * HW * C * 6 / ms / 1e6:7.1f} GB/s (algorithmic 4 B read + 2 B write)")
 
 
+def bench_elementwise():
+    """the fused CFG + DDIM update and the inverse-DDIM axpby: 128-bit loads / stores.  At the c3 latent size (4 x 4 x 128 x 128
+    fp32: 2 eps reads + x read + x write = 1 MiB) a launch is latency-bound, so the kernel's own bandwidth is shown on a size that
+    is not (same kernel, 256x the elements, buffers cycled through > L2)."""
+    for name, B, L, rep in [("c3 latents", 4, 128, 1), ("256 x c3 latents", 4, 128, 256)]:
+        n = B * 4 * L * L * rep
+        nb = 1 if rep == 1 else 3
+        eps2 = [torch.randn(2 * n, device=dev) for _ in range(nb)]
+        x = [torch.randn(n, device=dev) for _ in range(nb)]
+        out = torch.empty(n, device=dev)
+        f = lambda i: ops.cfg_ddim_step(eps2[i % nb].view(2, -1), x[i % nb].view(1, -1), 10.0, 0.99, -0.1, x_out=out.view(1, -1))
+        g = torch.cuda.CUDAGraph()
+        f(0)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            for i in range(nb * 4):
+                f(i)
+        ms = timeit(lambda i: g.replay(), iters=10) / (nb * 4)
+        print(f"cfg_ddim_step {name:18s}: {ms * 1e3:8.2f} us  {16.0 * n / ms / 1e6:8.1f} GB/s (2 eps reads + x read + x write, fp32)")
+        f2 = lambda i: ops.axpby(eps2[i % nb][:n], x[i % nb], 0.99, -0.1, out=out)
+        g2 = torch.cuda.CUDAGraph()
+        f2(0)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g2):
+            for i in range(nb * 4):
+                f2(i)
+        ms = timeit(lambda i: g2.replay(), iters=10) / (nb * 4)
+        print(f"axpby         {name:18s}: {ms * 1e3:8.2f} us  {12.0 * n / ms / 1e6:8.1f} GB/s (eps read + x read + x write, fp32)")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.manual_seed(0)
-    for k, fn in (("gemm", bench_gemm), ("conv", bench_conv), ("attn", bench_attn), ("norm", bench_norm), ("lnfold", bench_lnfold), ("mainloop", bench_mainloop), ("vae", bench_vae)):
+    for k, fn in (("gemm", bench_gemm), ("conv", bench_conv), ("attn", bench_attn), ("norm", bench_norm), ("elementwise", bench_elementwise), ("lnfold", bench_lnfold), ("mainloop", bench_mainloop), ("vae", bench_vae)):
         if which in (k, "all"):
             fn()
