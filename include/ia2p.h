@@ -137,6 +137,13 @@ int64_t ia2p_tc_workspace_bytes(void);
 int ia2p_tc_features(void);   /* experiment paths compiled into this build: bit 0 split-K, bit 1 A-operand multicast (0 in the shipped library) */
 int ia2p_set_tc_workspace(void* workspace, int64_t bytes);
 
+/* Programmatic dependent launch for the launches this host thread makes from now on: 1 = every kernel is launched with
+ * programmatic stream serialisation (its prologue -- and, in ia2p_gemm_smallm, its first weight loads -- overlap the tail of the
+ * previous kernel of the stream), 0 = off, -1 = the IA2P_PDL environment default (off).  Returns the previous mode.  The embedding
+ * prior (a chain of ~175 tiny dependent kernels per step, prior/model.py:624-626) turns it on around its trunk; the UNet step
+ * measured no gain from it (profiles/README.md). */
+int ia2p_set_pdl(int mode);
+
 /* One-shot hint for the NEXT ia2p_gemm_* / ia2p_conv* call made by this host thread: that launch also pulls `bytes` of
  * `next_weights` (the weight matrix of the tensor-core launch that will follow it) into L2, so the following kernel's first
  * wave does not start on cold DRAM misses (each layer's weights are touched once per step and never survive in L2).  The

@@ -22,6 +22,7 @@ SIGNATURES = {
     "ia2p_version": ([], _i),
     "ia2p_last_error": ([], C.c_char_p),
     "ia2p_device_check": ([_i], _i),
+    "ia2p_set_pdl": ([_i], _i),
     "ia2p_cfg_ddim_step": ([_p, _i, _p, _p, _i, _p, _i, _l, _l, _f, _f, _f, _p], _i),
     "ia2p_axpby": ([_p, _i, _p, _p, _i, _l, _f, _f, _p], _i),
     "ia2p_inpaint_blend": ([_p, _p, _p, _p, _p, _l, _l, _l, _f, _f, _p], _i),

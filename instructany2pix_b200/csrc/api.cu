@@ -46,7 +46,9 @@ int check_device() {
   return query_device(dev);
 }
 
+static thread_local int g_pdl_mode = -1;        // ia2p_set_pdl: -1 = the IA2P_PDL environment default, 0 = off, 1 = on
 bool pdl_enabled() {
+  if (g_pdl_mode >= 0) return g_pdl_mode != 0;
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("IA2P_PDL");
@@ -92,6 +94,11 @@ int make_map_3d_bf16(CUtensorMap* m, const void* base, int64_t cols, int64_t ld,
 }  // namespace ia2p
 
 extern "C" int ia2p_version(void) { return 100; }
+extern "C" int ia2p_set_pdl(int mode) {
+  const int prev = ia2p::g_pdl_mode;
+  ia2p::g_pdl_mode = mode < 0 ? -1 : (mode ? 1 : 0);
+  return prev;
+}
 extern "C" const char* ia2p_last_error(void) { return ia2p::g_err; }
 extern "C" int ia2p_device_check(int device) {
   if (device < 0) return ia2p::check_device();

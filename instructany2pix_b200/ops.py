@@ -103,6 +103,20 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+class pdl:
+    """``with ops.pdl():`` -- the launches inside use programmatic dependent launch (ia2p_set_pdl); restores the previous mode."""
+
+    def __init__(self, on=True):
+        self.on, self.prev = on, -1
+
+    def __enter__(self):
+        self.prev = _lib.load().ia2p_set_pdl(1 if self.on else 0)
+        return self
+
+    def __exit__(self, *a):
+        _lib.load().ia2p_set_pdl(self.prev)
+
+
 def _need(t, dtype, name, ndim=None):
     if not t.is_cuda:
         raise IA2PError(f"{name}: expected a CUDA tensor (instructany2pix_b200 has no CPU path)")

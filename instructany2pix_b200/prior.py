@@ -193,6 +193,10 @@ class B200Prior(nn.Module):
         """GPT2Model(inputs_embeds=seq)["last_hidden_state"][:, -1] -> [2*bs, E] fp32."""
         P = self.prepare()
         B2, T, E = seq.shape
+        with ops.pdl():      # ~175 tiny dependent kernels: each one's prologue / weight prefetch overlaps its predecessor's tail
+            return self._trunk_last_impl(P, seq, B2, T, E)
+
+    def _trunk_last_impl(self, P, seq, B2, T, E):
         h = ops.axpby(P["wpe"][:T].unsqueeze(0).expand(B2, T, E).contiguous(), seq, 1.0, 1.0).reshape(B2 * T, E)
         for L in P["layers"]:
             a = ops.layernorm(h, L["ln1"][0], L["ln1"][1], 1e-5)
