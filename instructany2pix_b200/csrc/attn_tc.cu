@@ -29,12 +29,16 @@ constexpr int kFaTile = 128 * 128;                 // bytes: 128 rows x 64 bf16
 constexpr int kFaSmemTiles = kFaTile * (1 + 2 + 2);       // Q, K x2, V x2
 constexpr int kFaSmemBytes = kFaSmemTiles + 1024;  // barriers live in the alignment slack in front of the tiles
 constexpr float kRescaleThreshold = 8.0f;
-// What bounds this kernel (measured, tools/trace_attn.py, tools/mmabench.cu, ncu): MMA ISSUE.  One tcgen05.mma (M 128, K 16) costs
-// max(94, N/2 + 38) cycles whatever it computes, so a 128 x 128 key block needs 4 x 102 (Q.K^T, N 128) + 8 x 94 (P.V, N 64) =
-// 1 163 cycles of the tensor pipe per CTA, 2 326 for the two co-resident CTAs; the kernel takes 2 435 (95 % of that floor).  The
-// softmax side (64 KB of S through tcgen05.ld, 16 384 exponentials on 16 SFU lanes: ~1 024 cycles per block and SM) is second,
-// which is why bf16 packing by truncation and evaluating every 4th exp2 on the FMA pipe (FlashAttention-4 style) did not help
-// (2 435 -> 2 751 cycles).  P.V cannot use a wider N (N = head_dim) nor more K per instruction (K = 16 for bf16).
+#ifndef IA2P_FA_POLY
+#define IA2P_FA_POLY 1      // share of the fast-path exponentials evaluated by ex2_poly3 instead of MUFU.EX2: 0 = none, 1 = 1/4, 2 = 1/2
+#endif
+// What bounds this kernel (measured, tools/trace_attn.py, ncu): the SOFTMAX, i.e. the SFU.  A 128 x 128 key block needs 16 384
+// exponentials; an SM has 16 MUFU lanes, so the two co-resident CTAs cannot finish a pair of blocks in less than 2 048 cycles, and
+// the kernel takes ~2 390 (the MMAs of a block are 512 cycles of tensor pipe per CTA once they are issued from uniform registers --
+// round 1's "94 cycles per tcgen05.mma issue floor" was the R2UR waterfall of a `lane == 0` issue loop, see common.cuh elect_one).
+// Hence IA2P_FA_POLY: every 4th exponential of the fast path is evaluated by ex2_poly3 on the FMA / ALU pipes (FlashAttention-4
+// style).  Measured on B200 (tools/bench_kernels.py attn): N 4096: 715 -> 829 TFLOP/s with 1/4 of them, 722 with 1/2 (issue-bound
+// again); N 1024: 579 -> 588 (8 key blocks per CTA: prologue and the 4.3-wave grid dominate there).
 #ifdef IA2P_TC_TRACE
 #define IA2P_TRACE_BUF g_fa_trace
 __device__ unsigned long long* g_fa_trace = nullptr;           // debug build: counters of the CTAs with blockIdx.y == z == 0
@@ -184,9 +188,17 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, neg_m));
+#if IA2P_FA_POLY >= 2
+            const float p1 = ex2_poly3(fmaf(__uint_as_float(v[i + 1]), scale_log2, neg_m));
+#else
             const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, neg_m));
+#endif
             const float p2 = ex2_approx(fmaf(__uint_as_float(v[i + 2]), scale_log2, neg_m));
+#if IA2P_FA_POLY >= 1
+            const float p3 = ex2_poly3(fmaf(__uint_as_float(v[i + 3]), scale_log2, neg_m));      // every 4th on the FMA pipe
+#else
             const float p3 = ex2_approx(fmaf(__uint_as_float(v[i + 3]), scale_log2, neg_m));
+#endif
             ls0 += p0 + p2;
             ls1 += p1 + p3;
             pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);

@@ -423,6 +423,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes instead of the SFU (Cody-Waite range reduction + a degree-3 minimax polynomial on [-0.5, 0.5],
+// max relative error 7.5e-5 -- far below the bf16 rounding the result gets in the attention kernels): x + 1.5 * 2^23 leaves
+// round(x) in the low mantissa bits, which are shifted straight into the exponent field of the polynomial's value.  Valid for
+// -125 <= x < 100 (smaller x is clamped).  The flash-attention softmax is bound by the 16 MUFU lanes of an SM; evaluating a
+// quarter of the exponentials here runs them on otherwise idle pipes (FlashAttention-4's trick).
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -125.f);
+  const float xf = x + 12582912.f;
+  const float f = x - (xf - 12582912.f);
+  float p = fmaf(0.0551716685f, f, 0.2426111400f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
