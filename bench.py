@@ -58,8 +58,8 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes (read + write) per tc_gemm_kernel launch, averaged over the 480 launches of one UNet step, from the committed
-    ncu capture (profiles/gemm_traffic_r01.json; not measured live -- a run under ncu is never a bench value)."""
-    p = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
+    ncu capture (profiles/gemm_traffic_r02.json; not measured live -- a run under ncu is never a bench value)."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic_r02.json")
     if os.path.exists(p):
         return json.load(open(p))["dram_bytes_per_launch"]
     return None
