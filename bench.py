@@ -574,6 +574,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG", "WARN")               # keep NCCL's version banner out of stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
+    torch.manual_seed(1234)                                       # every rank builds the SAME random-init weights (incl. default-init modules)
     if wl["L"] is None:
         bench_prior(args, wl, dev, rank, world, local)
         if world > 1:

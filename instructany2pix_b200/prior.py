@@ -248,10 +248,18 @@ class B200Prior(nn.Module):
                            generator=None, image_bind_overwrite=None, guidance_scale=5, score=6.8, negative_score=2.0,
                            do_classifier_free_guidance=True, device="cuda", dtype=torch.float16, no_diffusion=False,
                            force_guidence_t0=False, trace=None):
+        # Arguments of the reference signature (prior/model.py:527-541) and what they mean here:
+        #   do_classifier_free_guidance=False -> ``noise_pred = output`` of the conditional rows (:645-646).  The trunk is bound by
+        #       streaming its weights, rows are free: the unconditional rows are still evaluated and combined with weight 0
+        #       (guidance 1: eps_u + 1 * (eps_c - eps_u)), one code path, equal to the reference to an ulp.
+        #   eta -> reaches ``prepare_extra_step_kwargs`` only; [3P] ``DDPMScheduler.step`` takes no eta, so it is ignored there too.
+        #   image_bind_overwrite -> only read when the source is text (:558-566); for every other source it is overwritten by ``src``.
+        #   no_grad -> unused in the reference body as well.
         if not do_classifier_free_guidance:
-            raise NotImplementedError("the reference always calls the prior with classifier-free guidance (pipeline.py:313-317)")
+            guidance_scale = 1.0
         if src_type == 2:
-            raise NotImplementedError("text-source prior (MODALITY.TEXT) is not on the reference hot path")
+            raise NotImplementedError("text-source prior (MODALITY.TEXT, prior/model.py:554-556) needs the CLIP text tower on every call and is "
+                                      "never used by pipeline.py (it passes MODALITY.VIDEO at :313): not on the hot path")
         if no_diffusion:
             num_inference_steps = 1
         dev, E = self.device, self.embed_dim

@@ -67,3 +67,15 @@ def test_batched_prior_rows_match_per_sample_oracle(emu):
         finally:
             torch.randn = real_randn
         assert cos(yb[i], yo) > 0.9999
+
+
+def test_no_cfg_equals_conditional_prediction(emu):
+    """do_classifier_free_guidance=False (prior/model.py:645-646): the conditional prediction alone; here guidance weight 1"""
+    o, b = build(2)
+    src, clip_hidden = G.prior_inputs("l2_nodiff")
+    b.set_clip_hidden(clip_hidden)
+    torch.manual_seed(5)
+    y, _ = b.generate_diffusion(3, 0, src, device="cpu", dtype=torch.float32, no_diffusion=True, do_classifier_free_guidance=False, score=6.5)
+    torch.manual_seed(5)
+    yo, _ = o.generate_diffusion(3, 0, src, clip_hidden, no_diffusion=True, guidance_scale=1.0, score=6.5)
+    assert cos(y, yo) > 0.9999
