@@ -28,17 +28,26 @@ struct alignas(64) FaMaps {
 constexpr int kFaTile = 128 * 128;                 // bytes: 128 rows x 64 bf16
 constexpr int kFaSmemTiles = kFaTile * (1 + 2 + 2);       // Q, K x2, V x2
 constexpr int kFaSmemBytes = kFaSmemTiles + 1024;  // barriers live in the alignment slack in front of the tiles
-constexpr float kRescaleThreshold = 8.0f;
-#ifndef IA2P_FA_POLY
-#define IA2P_FA_POLY 1      // share of the fast-path exponentials evaluated by ex2_poly3 instead of MUFU.EX2: 0 = none, 1 = 1/4, 2 = 1/2
+#ifndef IA2P_FA_TRUNC
+#define IA2P_FA_TRUNC 1
 #endif
-// What bounds this kernel (measured, tools/trace_attn.py, ncu): the SOFTMAX, i.e. the SFU.  A 128 x 128 key block needs 16 384
-// exponentials; an SM has 16 MUFU lanes, so the two co-resident CTAs cannot finish a pair of blocks in less than 2 048 cycles, and
-// the kernel takes ~2 390 (the MMAs of a block are 512 cycles of tensor pipe per CTA once they are issued from uniform registers --
-// round 1's "94 cycles per tcgen05.mma issue floor" was the R2UR waterfall of a `lane == 0` issue loop, see common.cuh elect_one).
-// Hence IA2P_FA_POLY: every 4th exponential of the fast path is evaluated by ex2_poly3 on the FMA / ALU pipes (FlashAttention-4
-// style).  Measured on B200 (tools/bench_kernels.py attn): N 4096: 715 -> 829 TFLOP/s with 1/4 of them, 722 with 1/2 (issue-bound
-// again); N 1024: 579 -> 588 (8 key blocks per CTA: prologue and the 4.3-wave grid dominate there).
+#ifndef IA2P_FA_POLY16
+#define IA2P_FA_POLY16 5    // of every 16 key PAIRS of the fast path, this many get their exponentials from ex2_poly3_x2 instead of MUFU.EX2
+#endif
+// What bounds this kernel (measured: tools/sfubench.cu, tools/mmabench.cu "fa pattern", tools/trace_attn.py, profiles/ncu_fa_tc_r02.txt):
+//  * tensor pipe: S = Q K^T (4 x M128 N128 K16) and O += P V (8 x M128 N64 K16, A from TMEM) BOTH run at the full rate -- 256 + 256
+//    cycles per 128-key block and CTA, 1 036 per block of the two co-resident CTAs (the N = 64 MMAs are not slower per MAC);
+//  * softmax: the SM sub-partition dispatches one instruction per cycle, FFMA2 / FADD2 / F2FP occupy two slots, MUFU.EX2 one slot
+//    plus 8 cycles of the 4-lane SFU.  Per exponential: scale-subtract 1 + row sum 1 + pack 0.5..1 + (MUFU 1 | polynomial 7) slots,
+//    so ~6 cycles per exponential whatever the MUFU / polynomial split between 4/16 and 6/16 (sfubench "softmax mix" rows), i.e.
+//    >= 1 540 cycles per block of the CTA pair;
+//  * power: under this kernel the chip settles at ~1.54 GHz (1 kW cap), and that is what the variants converge to: one or two
+//    threads per row (4 or 8 softmax warps), S in 64-key halves with their own barriers, a staggered start of the co-resident CTAs,
+//    truncating or rounding the bf16 pack, 4/16 .. 8/16 polynomial share all land at 840-900 TFLOP/s at 4 096 tokens and 600-660 at
+//    1 024 (round 1: 725 / 550; scalar FFMA with 1/4 polynomial: 829 / 588).
+// Kept from those experiments: packed fp32 pairs (fewer registers: 126, no spills), P written to TMEM chunk by chunk, the
+// first block's reference taken from its first 32 keys (no separate max pass), truncating pack with the 2^-9 bias folded into
+// the reference, 5 of 16 pairs on the polynomial.
 #ifdef IA2P_TC_TRACE
 #define IA2P_TRACE_BUF g_fa_trace
 __device__ unsigned long long* g_fa_trace = nullptr;           // debug build: counters of the CTAs with blockIdx.y == z == 0
@@ -173,41 +182,66 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       tc_fence_after();
       const int kv_left = n_tokens - j * 128;                     // valid keys in this block (>= 1)
       const bool ragged = kv_left < 128;                          // only the last block can be ragged
-      uint32_t pk[64];
       float lsum = 0.f, alpha = 1.f;
-      // FAST PATH (every block but the first): one pass, p = 2^(s*scale - m_ref) against the standing reference max.
-      // bf16 / fp32 share the exponent range, so p may exceed 1 by many orders without harm; the reference is only
-      // raised when a row's block sum shows it is stale by > 2^20 (or on the first / ragged block) -> SLOW PATH below.
-      bool slow = (j == 0) || ragged;
+      // P (bf16 pairs) goes to TMEM chunk by chunk, 16 cells per 32 keys, so only one chunk of it is ever live in registers.  The P
+      // cells and the O accumulator are free once MMA2 of block j-1 has completed; that MMA was issued right behind MMA1 of this
+      // block, so by the first store (a chunk of exponentials after S arrived) the wait is normally over already.
+      bool pv_waited = (j == 0);
+      auto wait_pv_prev = [&]() {
+        if (!pv_waited) {
+          TRACE_T0(ts2);
+          mbar_wait(pv_full, (uint32_t)((j - 1) & 1));
+          tc_fence_after();
+          TRACE_ADD(tr_wait_pv, ts2);
+          pv_waited = true;
+        }
+      };
+      // FAST PATH: one pass, p = 2^(s*scale - m_ref) against the standing reference max.  bf16 / fp32 share the exponent
+      // range, so p may exceed 1 by many orders without harm; the reference is only raised when a row's block sum shows it is
+      // stale by > 2^20 (or on a ragged block) -> SLOW PATH below.
+      bool slow = ragged;
       if (!slow) {
         // chunk c + 1 is in flight from TMEM while the exponentials of chunk c are computed
         uint32_t va[32], vb[32];
-        float ls0 = 0.f, ls1 = 0.f;
-        const float neg_m = -m_ref;
-        auto soft32 = [&](const uint32_t (&v)[32], int c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, neg_m));
-#if IA2P_FA_POLY >= 2
-            const float p1 = ex2_poly3(fmaf(__uint_as_float(v[i + 1]), scale_log2, neg_m));
-#else
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, neg_m));
-#endif
-            const float p2 = ex2_approx(fmaf(__uint_as_float(v[i + 2]), scale_log2, neg_m));
-#if IA2P_FA_POLY >= 1
-            const float p3 = ex2_poly3(fmaf(__uint_as_float(v[i + 3]), scale_log2, neg_m));      // every 4th on the FMA pipe
-#else
-            const float p3 = ex2_approx(fmaf(__uint_as_float(v[i + 3]), scale_log2, neg_m));
-#endif
-            ls0 += p0 + p2;
-            ls1 += p1 + p3;
-            pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
-            pk[c * 16 + (i >> 1) + 1] = pack_bf16x2(p2, p3);
-          }
-        };
+        uint64_t ls0 = f2_pack(0.f, 0.f), ls1 = ls0;
         tmem_ld_32x32(tS + lane_sel, va);
         tmem_ld_wait();
         tmem_ld_32x32(tS + lane_sel + 32u, vb);
+        if (j == 0) {
+          // First block: ANY reference within ~2^20 of the row maximum will do (it cancels in O / l), so take the maximum of the
+          // first 32 keys instead of a separate max pass over all 128; a row whose later keys tower over it fails the sum check
+          // below and is redone on the slow path like any other stale reference.
+          float mx = __uint_as_float(va[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
+          m_ref = mx * scale_log2;
+        }
+        // IA2P_FA_TRUNC: p is produced a factor (1 + 2^-9) too large (folded into the reference) and TRUNCATED to bf16 by one
+        // byte permute per pair instead of a round-to-nearest F2FP (two issue slots): the error is the same +-2^-9 band, centred;
+        // the row sum of this block is divided by the factor again below.
+        const float nm = IA2P_FA_TRUNC ? 0.00281502f - m_ref : -m_ref;
+        const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(nm, nm);
+        auto soft32 = [&](const uint32_t (&v)[32], int c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {                          // pair i = keys 2i, 2i + 1 of this 32-key chunk
+            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+            uint64_t p2;
+            if (((i * IA2P_FA_POLY16) & 15) < IA2P_FA_POLY16) {   // IA2P_FA_POLY16 of every 16 pairs on the FMA / ALU pipes
+              p2 = ex2_poly3_x2(x2);
+            } else {
+              float x0, x1;
+              f2_unpack(x2, x0, x1);
+              p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+            }
+            if (i & 1) ls1 = f2_add(ls1, p2); else ls0 = f2_add(ls0, p2);
+            float p0, p1;
+            f2_unpack(p2, p0, p1);
+            pk[i] = IA2P_FA_TRUNC ? __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632) : pack_bf16x2(p0, p1);
+          }
+          wait_pv_prev();
+          tmem_st_32x16(tP + lane_sel + (uint32_t)(c * 16), pk);
+        };
         soft32(va, 0);
         tmem_ld_wait();
         tmem_ld_32x32(tS + lane_sel + 64u, va);
@@ -217,12 +251,18 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
         soft32(va, 2);
         tmem_ld_wait();
         soft32(vb, 3);
-        lsum = ls0 + ls1;
+        {
+          float a0, a1;
+          f2_unpack(f2_add(ls0, ls1), a0, a1);
+          lsum = a0 + a1;
+          if (IA2P_FA_TRUNC) lsum *= 0.998050682f;               // 1 / (1 + 2^-9)
+        }
         slow = !(lsum < 1048576.f);                               // also catches inf / nan
       }
       const bool any_slow = __any_sync(0xffffffffu, slow);
       if (any_slow) {
-        // SLOW PATH (warp-uniform): exact block row max -> raise the reference, recompute p, remember alpha for O and l
+        // SLOW PATH (warp-uniform): exact block row max -> raise the reference, rescale O and l, recompute p (overwrites whatever
+        // the fast path stored)
         float mx = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -238,9 +278,22 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
         m_ref = m_new;
         l *= alpha;
         lsum = 0.f;
+        tmem_st_wait();                                           // fast-path P stores of this block, if any, are about to be overwritten
+        wait_pv_prev();
+        if (j > 0) {                                              // rescale O row-wise in TMEM
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + lane_sel + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
 #pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(tO + lane_sel + (uint32_t)(c * 32), v);
+          }
+        }
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
+          uint32_t v[32], pk[16];
           tmem_ld_32x32(tS + lane_sel + (uint32_t)(c * 32), v);
           tmem_ld_wait();
 #pragma unroll
@@ -252,8 +305,9 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
               if (c * 32 + i + 1 >= kv_left) p1 = 0.f;
             }
             lsum += p0 + p1;
-            pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+            pk[i >> 1] = pack_bf16x2(p0, p1);
           }
+          tmem_st_32x16(tP + lane_sel + (uint32_t)(c * 16), pk);
         }
       }
       l += lsum;
@@ -261,34 +315,8 @@ fa_tc_kernel(const __grid_constant__ FaMaps maps, __nv_bfloat16* __restrict__ ou
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);                        // S may be overwritten by MMA1 of block j+1
       TRACE_ADD(tr_softmax, ts1);
-      TRACE_T0(ts2);
-      // P buffer / O accumulator are free once MMA2 of block j-1 has completed
-      if (j > 0) {
-        mbar_wait(pv_full, (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-        if (any_slow) {                                           // rare: reference raised -> rescale O row-wise in TMEM
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(tO + lane_sel + (uint32_t)(c * 32), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32(tO + lane_sel + (uint32_t)(c * 32), v);
-          }
-          tmem_st_wait();
-        }
-      }
-      TRACE_ADD(tr_wait_pv, ts2);
       TRACE_T0(ts3);
-      // P -> TMEM: this thread's row, 64 cells of two bf16 keys each (the A operand of MMA2)
-      {
-        uint32_t (&plo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
-        uint32_t (&phi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
-        tmem_st_32x32(tP + lane_sel, plo);
-        tmem_st_32x32(tP + lane_sel + 32u, phi);
-        tmem_st_wait();
-      }
+      tmem_st_wait();                                             // this row's P cells (the A operand of MMA2) have landed
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);

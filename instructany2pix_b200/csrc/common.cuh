@@ -437,6 +437,46 @@ __device__ __forceinline__ float ex2_poly3(float x) {
   p = fmaf(p, f, 0.9999280572f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two fp32 operations on an aligned 64-bit register pair).  The
+// flash-attention softmax is bound by ISSUE slots next to the MUFU lanes, so the scale-subtract, the row sum and the polynomial run
+// on pairs of neighbouring keys.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// ex2_poly3 on a pair: 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 shift-adds = 5 issue slots per exponential (scalar form: 8)
+__device__ __forceinline__ uint64_t ex2_poly3_x2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x2 = f2_pack(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const uint64_t magic = f2_pack(12582912.f, 12582912.f);
+  const uint64_t xf = f2_add(x2, magic);
+  const uint64_t f = f2_sub(x2, f2_sub(xf, magic));
+  uint64_t p = f2_fma(f2_pack(0.0551716685f, 0.0551716685f), f, f2_pack(0.2426111400f, 0.2426111400f));
+  p = f2_fma(p, f, f2_pack(0.6932609677f, 0.6932609677f));
+  p = f2_fma(p, f, f2_pack(0.9999280572f, 0.9999280572f));
+  float p0, p1, n0, n1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(xf, n0, n1);
+  return f2_pack(__int_as_float(__float_as_int(p0) + (__float_as_int(n0) << 23)), __int_as_float(__float_as_int(p1) + (__float_as_int(n1) << 23)));
+}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -446,6 +486,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(128, 1) mma_chain(int n, int mode, int iters, 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, slot = bar + 16, bar2 = bar + 8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  (void)lane;
   if ((int)blockIdx.x >= ctas_active) return;
   if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
   if (warp == 0) { tmem_alloc(slot, 512); tmem_relinquish(); }
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(128, 1) mma_chain(int n, int mode, int iters, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
-  if (warp == 1 && lane == 0) {
+  if (warp == 1 && elect_one()) {     // warp-uniform role + elect.sync lane: uniform-register operands (round 1 used lane == 0: R2UR waterfall, 158.8 clk flat)
     const uint32_t idesc = umma_idesc_bf16(128, n, mode == 1 ? 1 : 0);
     const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sB);
     const long long t0 = clock64();
@@ -158,10 +159,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) mma_ring_pai
   if (warp == 0) { tc_fence_after(); tmem_dealloc_2sm(tmem, 512); }
 }
 
+// The flash-attention kernel's tensor work per 128-key block and CTA, issued back to back with compile-time shapes (no run-time
+// mode branches in the issue loop): WHAT = 1: S = Q K^T as 4 x (M128 N128 K16, A smem); 2: O += P V as 8 x (M128 N64 K16, A tmem,
+// MN-major B); 3: both; 4: P V as N 128 (two heads' worth of V columns -- what a wider N would cost).  One or two CTAs per SM.
+template <int WHAT>
+__global__ void __launch_bounds__(128, 2) mma_fa_pattern(int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, slot = bar + 16;
+  const int warp = warp_idx_uniform();
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+  if (warp == 1 && elect_one()) {
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, WHAT == 4 ? 128 : 64, 1);
+    const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sB);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (WHAT & 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, 1u);
+      }
+      if (WHAT & 6) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16_ts(tmem + 128u, tmem + 192u + (uint32_t)(ks * 8), umma_desc_sw128_mn(sB + ks * 2048, 16384), idesc_pv, 1u);
+      }
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+template <int WHAT>
+static void run_fa_pattern(long long* d, int smem, const char* what) {
+  cudaFuncSetAttribute(mma_fa_pattern<WHAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int per_sm : {1, 2}) {
+    const int ctas = 148 * per_sm, iters = 2000;
+    for (int rep = 0; rep < 2; ++rep) mma_fa_pattern<WHAT><<<ctas, 128, smem>>>(iters, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("fa pattern %d: %s\n", WHAT, cudaGetErrorString(e)); return; }
+    long long h[296];
+    cudaMemcpy(h, d, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s = 0;
+    for (int i = 0; i < ctas; ++i) s += (double)h[i];
+    printf("fa pattern %-44s %d CTA/SM: %7.1f clk per 128-key block and CTA\n", what, per_sm, s / ctas / iters);
+  }
+}
+
 int main() {
   long long* d;
-  cudaMalloc(&d, 148 * sizeof(long long));
+  cudaMalloc(&d, 296 * sizeof(long long));
   const int smem = 16384 + 32768 + 1024 + 64;
+  run_fa_pattern<1>(d, smem, "QK^T: 4 x M128 N128 K16");
+  run_fa_pattern<2>(d, smem, "PV: 8 x M128 N64 K16 (A in TMEM)");
+  run_fa_pattern<3>(d, smem, "QK^T + PV");
+  run_fa_pattern<4>(d, smem, "PV at N128: 8 x M128 N128 K16 (A in TMEM)");
   cudaFuncSetAttribute(mma_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(mma_chain_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 2000;
