@@ -502,7 +502,8 @@ def bench_prior(args, wl, dev, rank, world, local):
     rec, ops.PROFILE = ops.PROFILE, None
     prior.use_cuda_graph = keep
     per_step_kernels = sum(ops._KERNELS_PER_CALL.get(r[0], 1) for r in rec)
-    trunk_ms = sum(r[2].elapsed_time(r[3]) for r in rec if r[0] in ("ia2p_gemm_smallm",))
+    trunk_ms = sum(r[2].elapsed_time(r[3]) for r in rec if r[0] in ("ia2p_gemm_smallm", "ia2p_prior_trunk"))
+    fused = any(r[0] == "ia2p_prior_trunk" for r in rec)
     # end to end: pinned host embedding -> device, sampling, result -> host (the reference call passes device='cpu': pipeline.py:313)
     sync_all()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -531,7 +532,8 @@ def bench_prior(args, wl, dev, rank, world, local):
                         includes="H2D of the LLM embedding, 25 CFG steps with the per-step noise drawn on the host like the reference call "
                                  "(device='cpu', pipeline.py:313) and copied in, D2H of the embedding"),
                gpu_launches=int(launches_eager + (args.steps * PRIOR_STEPS * per_step_kernels if prior.use_cuda_graph else 0)),
-               roofline=dict(kernel="gemm_smallm_kernel (GPT-2-medium trunk, M = 2 CFG rows x 14 tokens)", bound="hbm", achieved=ach, peak=pk["hbm"],
+               roofline=dict(kernel=("prior_trunk_kernel (the whole GPT-2-medium trunk of a step as one persistent cooperative kernel, 128 CTAs, grid "
+                                     "barriers between phases; " if fused else "gemm_smallm_kernel (GPT-2-medium trunk, ") + "M = 2 CFG rows x 14 tokens)", bound="hbm", achieved=ach, peak=pk["hbm"],
                              unit="GB/s", frac=ach / pk["hbm"], traffic=None, peak_source=pk["src"] + " hbm_gbs",
                              algorithmic_bytes_per_step=wbytes, launches_per_step=per_step_kernels, eager_trunk_gemm_ms_per_step=trunk_ms,
                              trunk_graph_replay_us=trunk_us, trunk_graph_gbs=None if not trunk_us else wbytes / (trunk_us * 1e-6) / 1e9,

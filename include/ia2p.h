@@ -249,6 +249,18 @@ int ia2p_gemm_smallm(const float* A, int64_t lda, const void* W, const float* bi
  * qkv: [batch, T, 3*E] (q | k | v), out: [batch, T, E].  Replaces GPT2Attention ([3P]). */
 int ia2p_causal_attn_small_f32(const float* qkv, float* out, int64_t batch, int64_t T, int heads, void* stream);
 
+/* The whole GPT-2-medium trunk of ONE prior step (GPT2Model(inputs_embeds=seq)["last_hidden_state"][:, -1], [3P], called at
+ * prior/model.py:624-626) as a single persistent cooperative kernel: wpe add, 24 x (LN1 -> c_attn -> causal attention -> c_proj +
+ * residual -> LN2 -> c_fc + gelu_new -> c_proj + residual), ln_f of the last token.  seq: [B2, T, E] fp32; wpe: [>= T, E] fp32;
+ * layer_ptrs: HOST array of 12 device pointers per layer (wqkv, wo, wfc, wpr as bf16 [out, in]; bqkv, bo, bfc, bpr, ln1 gamma,
+ * ln1 beta, ln2 gamma, ln2 beta as fp32); out: [B2, E] fp32.  E = 1024, heads = 16, T <= 32, n_layer <= 30.  workspace: 256-byte
+ * aligned, ia2p_prior_trunk_workspace_bytes(B2 * T) bytes, ZERO-INITIALISED ONCE by the caller (it holds the grid barrier state)
+ * and then reused from call to call.  Results are bit-reproducible (fixed summation order, no atomics on data). */
+int64_t ia2p_prior_trunk_workspace_bytes(int64_t rows);
+int ia2p_prior_trunk(const float* seq, const float* wpe, const void* const* layer_ptrs, int n_layer, const float* lnf_g,
+                     const float* lnf_b, int64_t B2, int64_t T, int64_t E, int heads, void* workspace, int64_t ws_bytes,
+                     float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,8 @@ SIGNATURES = {
     "ia2p_decoupled_cross_attn_bf16": ([_p, _l, _p, _p, _l, _i, _p, _p, _l, _i, _f, _p, _l, _l, _l, _i, _f, _p], _i),
     "ia2p_gemm_smallm": ([_p, _l, _p, _p, _p, _l, _p, _l, _l, _l, _l, _i, _i, _p], _i),
     "ia2p_causal_attn_small_f32": ([_p, _p, _l, _l, _i, _p], _i),
+    "ia2p_prior_trunk_workspace_bytes": ([_l], _l),
+    "ia2p_prior_trunk": ([_p, _p, _p, _i, _p, _p, _l, _l, _l, _i, _p, _l, _p, _p], _i),
 }
 
 _lib = None

@@ -72,6 +72,7 @@ struct TcParams {
   // once its first tile's loads are under way, so the next kernel's first wave does not start on cold DRAM misses.
   const char* pf_ptr;
   long long pf_bytes;
+  int early_b;           // programmatic dependent launch: issue the first weight loads ahead of griddepcontrol.wait
   int Wo, Ho, B;                   // output pixel grid (plain GEMM: Wo = M, Ho = B = 1)
   int N;                           // GEMM N (pre-GEGLU)
   int rows_per_batch;              // rowbias row = pixel / rows_per_batch
@@ -301,7 +302,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (CG == 2 || mc > 1) cluster_sync_all(); else __syncthreads();   // peer barriers must be initialised before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_wait();                                                   // everything above overlapped the previous kernel's tail
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  The producer warp waits later: it
+  // first issues the WEIGHT loads of its first k-blocks (p.early_b: the B operand is never written by a kernel of the same stream)
+  const bool early_b = p.early_b != 0 && mc == 1;
+  if (warp != 0 || !early_b) pdl_wait();
 #ifdef IA2P_TC_TRACE
   if (warp == 0) TRACE_PUT(1, gtime_ns());
   if (threadIdx.x == 0 && g_tc_timeline != nullptr) atomicMin(g_tc_timeline + 2 * (size_t)p.trace_id, gtime_ns());
@@ -332,6 +336,33 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int mc_x = mc_row0 & ((1 << p.tw_log2) - 1);
     const int mc_y = (mc_row0 >> p.tw_log2) & ((1 << p.th_log2) - 1);
     const int mc_b = mc_row0 >> (p.tw_log2 + p.th_log2);
+    // early_b: the first min(STAGES, k-blocks) stages of the first tile get their arrive + B (weight) load here, BEFORE
+    // griddepcontrol.wait; the main loop below then only adds the A load for those stages.
+    int pre = 0;
+    if (early_b && !splitk && unit0 < total_tiles) {
+      const TcItem ti = tc_decode_item(p, unit0, BLOCK_N);
+      const int n0 = ti.n_tile * BLOCK_N + ti.n_off + (int)rank * (ti.w / CG);
+      const CUtensorMap* wm = (ti.w == BLOCK_N) ? &maps.w : &maps.w2;
+      const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + (ti.w / CG) * 128);
+      for (int e = 0; e < p.ntaps && pre < STAGES; ++e) {
+        const TapEntry t = p.taps[e];
+        for (int c = 0; c < t.nchunks && pre < STAGES; ++c, ++pre) {
+          if (elect_one()) {
+            const uint32_t a_dst = smem_base + pre * Cfg::STAGE_BYTES;
+            if (CG == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(pre), 2 * stage_tx);
+              tma_load_2d_2sm(a_dst + Cfg::A_BYTES, wm, full_bar(pre), t.wk0 + c * 64, n0);
+            } else {
+              mbar_arrive_expect_tx(full_bar(pre), stage_tx);
+              tma_load_2d(a_dst + Cfg::A_BYTES, wm, full_bar(pre), t.wk0 + c * 64, n0);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (early_b) pdl_wait();
+    int issued = 0;                                     // k-blocks issued so far by this CTA
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const TcItem ti = tc_decode_item(p, tile, BLOCK_N);
       const int m_tile = ti.m_unit * CG + (int)rank;    // may be == m_tiles for the odd tail: TMA zero-fills (batch coord OOB)
@@ -348,10 +379,18 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const CUtensorMap* am = &maps.a[t.map_id];
         for (int c = 0; c < t.nchunks; ++c, ++kbi) {
           if (kbi < kb0 || kbi >= kb1) continue;          // split-K: another CTA owns this k-block
+          const bool b_done = issued < pre;               // arrive + B load already issued ahead of griddepcontrol.wait
+          ++issued;
           TRACE_T0(tw0);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           TRACE_ADD(tr_wait_empty, tw0);
-          if (elect_one()) {
+          if (b_done) {
+            if (elect_one()) {
+              const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+              if (CG == 2) tma_load_4d_2sm(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
+              else tma_load_4d(a_dst, am, full_bar(stage), c * 64, x0 + t.dx, y0 + t.dy, b0);
+            }
+          } else if (elect_one()) {
             const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
             if (CG == 2) {
               // Both CTAs' loads complete on the LEADER's full barrier (peer-bit-masked address).  Only the leader arrives
@@ -1308,6 +1347,7 @@ static int launch_tc(const TcMaps& maps, TcParams& p, cudaStream_t st) {
 #ifdef IA2P_TC_TRACE
   p.trace_id = g_tc_launch_id++;
 #endif
+  p.early_b = pdl_enabled() ? 1 : 0;
   p.pf_ptr = static_cast<const char*>(g_pf_ptr);       // one-shot hint: consumed by this launch
   p.pf_bytes = g_pf_bytes;
   g_pf_ptr = nullptr;

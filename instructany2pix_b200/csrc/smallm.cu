@@ -16,12 +16,11 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// (x, y) -> hi + lo bf16 pairs.  One packed F2FP per term and two bit operations to read the rounded halves back: the scalar
+// __float2bfloat16_rn compiles to F2F on the 16-lane conversion unit (8 cycles per warp instruction, 32 of them per k-step).
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
-  const float xr = x - __bfloat162float(xh), yr = y - __bfloat162float(yh);
-  __nv_bfloat162 h2; h2.x = xh; h2.y = yh;
-  hi = *reinterpret_cast<uint32_t*>(&h2);
-  lo = pack_bf16x2(xr, yr);
+  hi = pack_bf16x2(x, y);
+  lo = pack_bf16x2(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xffff0000u));
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -219,6 +218,374 @@ __global__ void causal_attn_small_kernel(const float* __restrict__ qkv, float* _
   *reinterpret_cast<float2*>(out + (b * T + i) * (long long)E + h * 64 + 2 * lane) = make_float2(o0 / sum, o1 / sum);
 }
 
+
+// ---------------------------------------------------------------- the whole GPT-2 trunk of one prior step as ONE persistent kernel
+// prior/model.py:624-626 runs GPT2Model on 2 x (11 | 14) rows per DDPM step: 7 ops x 24 layers = 175 dependent launches of ~8 us on
+// the per-op kernels above, against 92 us of weight streaming.  Here 128 CTAs (one per SM, cooperative launch) walk the layers
+// together and meet at a grid-wide barrier between phases:
+//   prologue  h = seq + wpe
+//   P1  qkv = LN1(h) Wqkv^T + b          CTA c: 24 of the 3 072 columns, K = 1 024 over the 8 warps
+//   P2  att = causal softmax(q k^T / 8) v                    one (sequence, head) item per CTA
+//   P3  h += att Wo^T + b                CTA c: 8 of 1 024 columns
+//   P4  f = gelu_new(LN2(h) Wfc^T + b)   CTA c: 32 of 4 096 columns
+//   P5  h += f Wpr^T + b                 CTA c: 8 of 1 024 columns, K = 4 096
+//   final     out[b] = ln_f(h[b, T - 1])
+// Every CTA owns whole output COLUMNS over the full K, so there is no split-K exchange between CTAs: the 8 warps of a CTA split K,
+// their partial tiles are summed through shared memory in warp order (bit-reproducible).  Weights are STATIONARY per phase: a
+// lane's 16-byte weight loads of the next phase are issued BEFORE the barrier that ends the current one, so the HBM latency hides
+// behind the barrier.  A (fp32, 32 rows at a time, written by other SMs in the previous phase) is staged through L2 by cp.async.cg
+// with every load of a phase in flight at once, and turned into hi + lo bf16 mma.sync fragments on the way to the tensor cores;
+// LayerNorm is folded into that (exact two-pass row statistics over the staged rows, gamma / beta per k).  Row counts above 32
+// (batched requests) reuse the resident weights.  First version (A fragments loaded straight from L2 per k-step, row statistics
+// from per-CTA partial sums, value loads of the attention in a run-time loop): 1 282 us per step -- one L2 round trip per k-step.
+constexpr int kPtCtas = 128, kPtThreads = 256, kPtMaxLayers = 30, kPtE = 1024;
+
+struct PtLayer {
+  const __nv_bfloat16 *wqkv, *wo, *wfc, *wpr;
+  const float *bqkv, *bo, *bfc, *bpr, *g1, *b1, *g2, *b2;
+};
+struct PtParams {
+  PtLayer layer[kPtMaxLayers];
+  const float *seq, *wpe, *gf, *bf;
+  float *h, *qkv, *att, *f, *out;
+  unsigned long long* bar;   // arrival counter (zero-initialised once, then only ever incremented)
+  int n_layer, B2, T, rows, rows_pad;
+};
+
+// Grid barrier: ONE 64-bit arrival counter that only ever grows (never reset, so there is no reset / generation hand-shake on the
+// critical path): barrier k of a launch is passed once the counter reaches base + (k + 1) * gridDim.x, where base is the value the
+// counter had when the launch began (a multiple of gridDim.x: every launch adds the same whole number of rounds; a CTA recovers it
+// by rounding down whatever it reads before its first arrival).  Arrive = one atom.add.release.gpu by thread 0 after the CTA's
+// bar.sync (cumulative: the whole CTA's writes are ordered before it), wait = ld.acquire.gpu polling.  All kPtCtas CTAs are
+// co-resident (cooperative launch); the wait is bounded, a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long pt_ld_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void pt_grid_sync(unsigned long long* bar, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
+    const long long t0 = clock64();
+    while (pt_ld_acquire(bar) < target) {
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+}
+#ifdef IA2P_TC_TRACE
+__device__ unsigned long long* g_pt_trace = nullptr;           // debug build: globaltimer stamps of CTA 0, one per phase boundary
+#define PT_STAMP() do { if (g_pt_trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_pt_trace[pt_n++] = gtime_ns(); } while (0)
+#else
+#define PT_STAMP()
+#endif
+
+template <int NT, int NS>
+__device__ __forceinline__ void pt_prefetch_w(uint4 (&wv)[NT * NS], const __nv_bfloat16* __restrict__ W, int n0, int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int k_lo = warp * (K >> 3);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+      wv[nt * NS + j] = __ldg(reinterpret_cast<const uint4*>(W + (long long)(n0 + nt * 8 + g) * K + k_lo + j * 32 + t * 8));
+}
+
+__device__ __forceinline__ void cp_async_cg16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;                                 // src-size 0: the 16 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// A staging: a ring of kPtRing slots; a slot holds two 32-wide k-steps of every warp's k-slice for a 32-row chunk: [8 warps][32 rows]
+// [64 fp32 + 4 pad] (272-byte rows: the 16-byte fragment reads of a quarter warp fall into different bank groups).
+constexpr int kPtRing = 3, kPtRowB = 272, kPtWarpB = 32 * kPtRowB, kPtSlotB = 8 * kPtWarpB;
+
+// One GEMM phase of this CTA: out[rows, n0 .. n0 + 8 NT) over K = 256 NS with the weights already in registers.  A (written by
+// other SMs in the previous phase) comes through L2 by cp.async.cg, every load of up to three slots in flight at once: one L2
+// round trip per phase instead of one per k-step.  LN (NS == 4: the whole chunk is resident): row mean / rstd from the staged rows
+// (two passes, exact), A = (A - mean) rstd gamma + beta applied while the fragments are built.
+template <int NT, int NS, bool LN>
+__device__ __forceinline__ void pt_gemm_phase(const PtParams& p, const uint4 (&wv)[NT * NS], const float* __restrict__ A, int lda,
+                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                              const float* __restrict__ bias, int act, const float* residual, float* out, int ldo,
+                                              int n0, uint8_t* s_ring, float* s_mean, float* s_rstd, float* s_part, float* s_gb) {
+  constexpr int K = NS * 256, NC = NT * 8, NR = NS / 2;          // NR rounds of two k-steps
+  static_assert(!LN || NR <= kPtRing, "LayerNorm needs the whole row chunk resident");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int k_lo = warp * (K >> 3);
+  const uint32_t ring = smem_u32(s_ring);
+  float* s_red = reinterpret_cast<float*>(s_ring);               // the reduction buffer reuses slot 0 once the MMAs are done
+  for (int m0 = 0; m0 < p.rows; m0 += 32) {
+    auto issue = [&](int round) {                                // this warp's 32 rows x 64 k of round `round`: 16 x 16 B per lane
+      const uint32_t dst = ring + (uint32_t)((round % kPtRing) * kPtSlotB + warp * kPtWarpB);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int q = i * 32 + lane, row = q >> 4, c4 = q & 15;
+        const bool ok = m0 + row < p.rows;
+        cp_async_cg16(dst + (uint32_t)(row * kPtRowB + c4 * 16), A + (long long)(ok ? m0 + row : 0) * lda + k_lo + round * 64 + c4 * 4, ok);
+      }
+      cp_async_commit();
+    };
+    if (LN && m0 == 0) {                                         // gamma | beta of the phase: 2 x 4 KB, same cp.async group as round 0
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = i * kPtThreads + threadIdx.x;              // 512 x 16 B
+        cp_async_cg16(smem_u32(s_gb) + (uint32_t)q * 16u, (q < 256 ? gamma : beta - kPtE) + q * 4, true);
+      }
+    }
+    // NT == 1 phases add the residual: its one value per thread is requested now, not after the reduction
+    float res_pref = 0.f;
+    if (NT == 1 && residual != nullptr && m0 + (threadIdx.x >> 3) < p.rows)
+      res_pref = __ldcg(residual + (long long)(m0 + (threadIdx.x >> 3)) * ldo + n0 + (threadIdx.x & 7));
+#pragma unroll
+    for (int r = 0; r < kPtRing; ++r)
+      if (r < NR) issue(r);
+    if (LN) {
+      cp_async_wait<0>();
+      __syncthreads();
+      // thread (warp w, lane r): the 128 values of row r staged by warp w (two slots) -- neighbouring lanes read neighbouring rows
+      // (272-byte pitch: conflict-free 16-byte reads; one thread per (row, region) pair with 8 lanes per row was an 8-way bank
+      // conflict on every load and cost 7 us per phase); the 8 regions' partials meet in shared memory, summed in region order
+      const uint8_t* base = s_ring + warp * kPtWarpB + lane * kPtRowB;
+      float sa = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(base + sl * kPtSlotB + i * 16);
+          sa += (v.x + v.y) + (v.z + v.w);
+        }
+      s_part[warp * 32 + lane] = sa;
+      __syncthreads();
+      float mean = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) mean += s_part[w * 32 + lane];
+      mean *= (1.f / kPtE);
+      __syncthreads();
+      float sq = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(base + sl * kPtSlotB + i * 16);
+          const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+          sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+      s_part[warp * 32 + lane] = sq;
+      __syncthreads();
+      if (warp == 0) {
+        float q = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) q += s_part[w * 32 + lane];
+        s_mean[lane] = mean;
+        s_rstd[lane] = rsqrtf(q * (1.f / kPtE) + 1e-5f);
+      }
+      __syncthreads();
+    }
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+    float mean_r[4], rstd_r[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      mean_r[r] = LN ? s_mean[g + 8 * r] : 0.f;
+      rstd_r[r] = LN ? s_rstd[g + 8 * r] : 1.f;
+    }
+#pragma unroll
+    for (int round = 0; round < NR; ++round) {
+      if (!LN) {                                                 // rounds complete in order; later ones stay in flight
+        if (NR - 1 - round >= 2) cp_async_wait<2>();
+        else if (NR - 1 - round == 1) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncwarp();
+      }
+      const uint8_t* slot = s_ring + (round % kPtRing) * kPtSlotB + warp * kPtWarpB;
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int j = round * 2 + s2;
+        float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), gb = ga, ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+        if (LN) {
+          const int k = k_lo + j * 32 + t * 8;
+          ga = *reinterpret_cast<const float4*>(s_gb + k); gb = *reinterpret_cast<const float4*>(s_gb + k + 4);
+          ba = *reinterpret_cast<const float4*>(s_gb + kPtE + k); bb = *reinterpret_cast<const float4*>(s_gb + kPtE + k + 4);
+        }
+        uint4 ah[4], al[4];                                      // rows g, g + 8, g + 16, g + 24: 8 consecutive k, hi and lo
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4* ap = reinterpret_cast<const float4*>(slot + (g + 8 * r) * kPtRowB + s2 * 128 + t * 32);
+          float4 x0 = ap[0], x1 = ap[1];
+          if (LN) {                                              // rows past p.rows are zero-filled: their results are never stored
+            const float mu = mean_r[r], rs = rstd_r[r];
+            x0.x = (x0.x - mu) * rs * ga.x + ba.x; x0.y = (x0.y - mu) * rs * ga.y + ba.y;
+            x0.z = (x0.z - mu) * rs * ga.z + ba.z; x0.w = (x0.w - mu) * rs * ga.w + ba.w;
+            x1.x = (x1.x - mu) * rs * gb.x + bb.x; x1.y = (x1.y - mu) * rs * gb.y + bb.y;
+            x1.z = (x1.z - mu) * rs * gb.z + bb.z; x1.w = (x1.w - mu) * rs * gb.w + bb.w;
+          }
+          split_pair(x0.x, x0.y, ah[r].x, al[r].x);
+          split_pair(x0.z, x0.w, ah[r].y, al[r].y);
+          split_pair(x1.x, x1.y, ah[r].z, al[r].z);
+          split_pair(x1.z, x1.w, ah[r].w, al[r].w);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const uint4 w = wv[nt * NS + j];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma_bf16_16816(acc[mt][nt], ah[2 * mt].x, ah[2 * mt + 1].x, ah[2 * mt].y, ah[2 * mt + 1].y, w.x, w.y);
+            mma_bf16_16816(acc[mt][nt], al[2 * mt].x, al[2 * mt + 1].x, al[2 * mt].y, al[2 * mt + 1].y, w.x, w.y);
+            mma_bf16_16816(acc[mt][nt], ah[2 * mt].z, ah[2 * mt + 1].z, ah[2 * mt].w, ah[2 * mt + 1].w, w.z, w.w);
+            mma_bf16_16816(acc[mt][nt], al[2 * mt].z, al[2 * mt + 1].z, al[2 * mt].w, al[2 * mt + 1].w, w.z, w.w);
+          }
+        }
+      }
+      if (round + kPtRing < NR) {                                // refill this slot (the warp's own region: a warp-level hand-over)
+        __syncwarp();
+        issue(round + kPtRing);
+      }
+    }
+    // the 8 warps' k-slice partials -> shared memory [warp][32 rows][NC + 1] (over slot 0), summed in warp order
+    constexpr int PP = NC + 1;
+    __syncthreads();                                             // every warp is done reading the ring
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float* d = s_red + ((size_t)warp * 32 + 16 * mt + 8 * hf + g) * PP + nt * 8 + 2 * t;
+          d[0] = acc[mt][nt][2 * hf];
+          d[1] = acc[mt][nt][2 * hf + 1];
+        }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * NC; idx += kPtThreads) {
+      const int row = idx / NC, col = idx - row * NC;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += s_red[((size_t)w * 32 + row) * PP + col];
+      const int m = m0 + row, n = n0 + col;
+      if (m < p.rows) {
+        v += __ldg(bias + n);
+        v = apply_act(v, act);
+        if (residual != nullptr) v += (NT == 1) ? res_pref : __ldcg(residual + (long long)m * ldo + n);
+        out[(long long)m * ldo + n] = v;
+      }
+    }
+    __syncthreads();                                             // s_red (slot 0) / s_mean are reused by the next row chunk
+  }
+}
+
+__global__ void __launch_bounds__(kPtThreads, 1) prior_trunk_kernel(const __grid_constant__ PtParams p) {
+  extern __shared__ __align__(16) uint8_t s_ring[];             // kPtRing x kPtSlotB
+  __shared__ float s_mean[32], s_rstd[32], s_part[8 * 32];
+  __shared__ __align__(16) float s_gb[2 * kPtE];
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int E = kPtE, T = p.T;
+  uint4 wq[12], wo[4], wf[16], wp[16];
+  unsigned long long bar_target = pt_ld_acquire(p.bar) / gridDim.x * gridDim.x;   // this launch's base; + gridDim.x per barrier
+#ifdef IA2P_TC_TRACE
+  int pt_n = 0;
+#endif
+  PT_STAMP();
+  pt_prefetch_w<3, 4>(wq, p.layer[0].wqkv, 24 * c, E);
+  // ---- prologue: h = seq + wpe (row r = (b, t) takes position t), CTA c owns columns [8c, 8c + 8)
+  for (int m0 = 0; m0 < p.rows; m0 += 32) {
+    const int row = m0 + (threadIdx.x >> 3), n = 8 * c + (threadIdx.x & 7);
+    const bool ok = row < p.rows;
+    if (ok) p.h[(long long)row * E + n] = __ldg(p.seq + (long long)row * E + n) + __ldg(p.wpe + (long long)(row % T) * E + n);
+  }
+  for (int l = 0; l < p.n_layer; ++l) {
+    const PtLayer& L = p.layer[l];
+    PT_STAMP();
+    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    PT_STAMP();
+    pt_gemm_phase<3, 4, true>(p, wq, p.h, E, L.g1, L.b1, L.bqkv, IA2P_ACT_NONE, nullptr, p.qkv, 3 * E, 24 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
+    pt_prefetch_w<1, 4>(wo, L.wo, 8 * c, E);
+    PT_STAMP();
+    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    PT_STAMP();
+    // ---- P2: causal attention, one (batch row block b, head) item per CTA, one query per warp; lane j owns key j
+    // (sequence b, head, query i) triples are dealt out one per WARP over the whole grid (32 heads-items x T queries: 448 warps' worth
+    // of work at batch 1; one item per CTA left 96 of the 128 CTAs idle and the phase 6 us long)
+    for (int wi = c * 8 + warp; wi < p.B2 * 16 * T; wi += gridDim.x * 8) {
+      {
+        const int item = wi / T, i = wi - item * T;
+        const int b = item >> 4, hd = item & 15;
+        const float* base = p.qkv + (long long)b * T * 3 * E + hd * 64;
+        const float4* qp = reinterpret_cast<const float4*>(base + (long long)i * 3 * E);
+        const bool live = lane <= i;
+        const float4* kp = reinterpret_cast<const float4*>(base + (long long)(live ? lane : 0) * 3 * E + E);
+        float sc = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          const float4 q4 = __ldcg(qp + d), k4 = __ldcg(kp + d);
+          sc += q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+        }
+        sc = live ? sc * 0.125f : -INFINITY;
+        const float mx = warp_max(sc);
+        const float pr = live ? __expf(sc - mx) : 0.f;
+        const float sum = warp_sum(pr);
+        float o0 = 0.f, o1 = 0.f;
+        const float* vb = base + 2 * E + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j <= i) {                                          // warp-uniform; unrolled: the value loads are independent
+            const float pj = __shfl_sync(0xffffffffu, pr, j);
+            const float2 vv = __ldcg(reinterpret_cast<const float2*>(vb + (long long)j * 3 * E));
+            o0 += pj * vv.x;
+            o1 += pj * vv.y;
+          }
+        }
+        *reinterpret_cast<float2*>(p.att + ((long long)b * T + i) * E + hd * 64 + 2 * lane) = make_float2(o0 / sum, o1 / sum);
+      }
+    }
+    PT_STAMP();
+    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    PT_STAMP();
+    pt_gemm_phase<1, 4, false>(p, wo, p.att, E, nullptr, nullptr, L.bo, IA2P_ACT_NONE, p.h, p.h, E, 8 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
+    pt_prefetch_w<4, 4>(wf, L.wfc, 32 * c, E);
+    PT_STAMP();
+    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    PT_STAMP();
+    pt_gemm_phase<4, 4, true>(p, wf, p.h, E, L.g2, L.b2, L.bfc, IA2P_ACT_GELU_NEW, nullptr, p.f, 4 * E, 32 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
+    pt_prefetch_w<1, 16>(wp, L.wpr, 8 * c, 4 * E);
+    PT_STAMP();
+    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    PT_STAMP();
+    pt_gemm_phase<1, 16, false>(p, wp, p.f, 4 * E, nullptr, nullptr, L.bpr, IA2P_ACT_NONE, p.h, p.h, E, 8 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
+    if (l + 1 < p.n_layer) pt_prefetch_w<3, 4>(wq, p.layer[l + 1].wqkv, 24 * c, E);
+  }
+  PT_STAMP();
+  pt_grid_sync(p.bar, bar_target += gridDim.x);
+  PT_STAMP();
+  // ---- final: out[b] = ln_f(h[b, T - 1]); one CTA per row, two-pass statistics, 4 elements per thread
+  for (int b = c; b < p.B2; b += gridDim.x) {
+    const float4 x = __ldcg(reinterpret_cast<const float4*>(p.h + ((long long)b * T + T - 1) * E) + threadIdx.x);
+    float s = warp_sum(x.x + x.y + x.z + x.w);
+    if (lane == 0) s_mean[warp] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_mean[w];
+    const float mean = tot / E;
+    const float dx = x.x - mean, dy = x.y - mean, dz = x.z - mean, dw = x.w - mean;
+    float q = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw);
+    if (lane == 0) s_rstd[warp] = q;
+    __syncthreads();
+    float qt = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) qt += s_rstd[w];
+    const float rstd = rsqrtf(qt / E + 1e-5f);
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gf) + threadIdx.x), bt = __ldg(reinterpret_cast<const float4*>(p.bf) + threadIdx.x);
+    *(reinterpret_cast<float4*>(p.out + (long long)b * E) + threadIdx.x) =
+        make_float4(dx * rstd * gm.x + bt.x, dy * rstd * gm.y + bt.y, dz * rstd * gm.z + bt.z, dw * rstd * gm.w + bt.w);
+    __syncthreads();
+  }
+}
 }  // namespace ia2p
 
 using namespace ia2p;
@@ -272,3 +639,63 @@ extern "C" int ia2p_causal_attn_small_f32(const float* qkv, float* out, int64_t 
   IA2P_LAUNCH_CHECK();
   return 0;
 }
+
+extern "C" int64_t ia2p_prior_trunk_workspace_bytes(int64_t rows) {
+  const int64_t rp = (rows + 31) / 32 * 32;
+  return 256 + rp * kPtE * 4 * (1 + 3 + 1 + 4);
+}
+
+extern "C" int ia2p_prior_trunk(const float* seq, const float* wpe, const void* const* layer_ptrs, int n_layer, const float* lnf_g,
+                                const float* lnf_b, int64_t B2, int64_t T, int64_t E, int heads, void* workspace, int64_t ws_bytes,
+                                float* out, void* stream) {
+  if (int e = check_device()) return e;
+  IA2P_REQUIRE(seq && wpe && layer_ptrs && lnf_g && lnf_b && workspace && out, IA2P_E_ARG, "prior_trunk: null argument");
+  IA2P_REQUIRE(E == kPtE && heads == 16, IA2P_E_SHAPE, "prior_trunk: the fused trunk is GPT-2-medium only (E=%lld heads=%d; need 1024 / 16)", (long long)E, heads);
+  IA2P_REQUIRE(n_layer >= 1 && n_layer <= kPtMaxLayers, IA2P_E_SHAPE, "prior_trunk: n_layer=%d not in [1,%d]", n_layer, kPtMaxLayers);
+  IA2P_REQUIRE(T >= 1 && T <= 32 && B2 >= 1, IA2P_E_SHAPE, "prior_trunk: T=%lld must be in [1,32]", (long long)T);
+  const int64_t rows = B2 * T, rp = (rows + 31) / 32 * 32;
+  IA2P_REQUIRE(ws_bytes >= ia2p_prior_trunk_workspace_bytes(rows), IA2P_E_ARG, "prior_trunk: workspace too small");
+  IA2P_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, IA2P_E_ALIGN, "prior_trunk: workspace must be 256-byte aligned");
+  IA2P_REQUIRE(sm_count() >= kPtCtas, IA2P_E_DEVICE, "prior_trunk: needs %d SMs", kPtCtas);
+  PtParams p{};
+  for (int l = 0; l < n_layer; ++l) {
+    const void* const* q = layer_ptrs + 12 * l;
+    for (int i = 0; i < 12; ++i) IA2P_REQUIRE(q[i] != nullptr && (reinterpret_cast<uintptr_t>(q[i]) & 15) == 0, IA2P_E_ALIGN, "prior_trunk: layer %d pointer %d null or not 16-byte aligned", l, i);
+    PtLayer& L = p.layer[l];
+    L.wqkv = static_cast<const __nv_bfloat16*>(q[0]); L.wo = static_cast<const __nv_bfloat16*>(q[1]);
+    L.wfc = static_cast<const __nv_bfloat16*>(q[2]); L.wpr = static_cast<const __nv_bfloat16*>(q[3]);
+    L.bqkv = static_cast<const float*>(q[4]); L.bo = static_cast<const float*>(q[5]); L.bfc = static_cast<const float*>(q[6]);
+    L.bpr = static_cast<const float*>(q[7]); L.g1 = static_cast<const float*>(q[8]); L.b1 = static_cast<const float*>(q[9]);
+    L.g2 = static_cast<const float*>(q[10]); L.b2 = static_cast<const float*>(q[11]);
+  }
+  char* ws = static_cast<char*>(workspace);
+  p.bar = reinterpret_cast<unsigned long long*>(ws);
+  float* f = reinterpret_cast<float*>(ws + 256);
+  p.h = f; f += rp * kPtE;
+  p.qkv = f; f += rp * kPtE * 3;
+  p.att = f; f += rp * kPtE;
+  p.f = f;
+  p.seq = seq; p.wpe = wpe; p.gf = lnf_g; p.bf = lnf_b; p.out = out;
+  p.n_layer = n_layer; p.B2 = (int)B2; p.T = (int)T; p.rows = (int)rows; p.rows_pad = (int)rp;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kPtCtas);
+  cfg.blockDim = dim3(kPtThreads);
+  cfg.dynamicSmemBytes = kPtRing * kPtSlotB;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  IA2P_ONCE_PER_DEVICE(IA2P_CUDA(cudaFuncSetAttribute(prior_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtRing * kPtSlotB)));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;          // all 128 CTAs co-resident, or the launch fails: the grid barrier cannot hang
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IA2P_CUDA(cudaLaunchKernelEx(&cfg, prior_trunk_kernel, p));
+  IA2P_LAUNCH_CHECK();
+  return 0;
+}
+
+#ifdef IA2P_TC_TRACE
+extern "C" int ia2p_debug_set_pt_trace(void* dev_buffer) {     // debug build only; not part of include/ia2p.h
+  unsigned long long* q = static_cast<unsigned long long*>(dev_buffer);
+  return (int)cudaMemcpyToSymbol(ia2p::g_pt_trace, &q, sizeof(q));
+}
+#endif

@@ -647,3 +647,34 @@ def causal_attn_small(qkv, batch, T, heads, out=None):
         out = torch.empty(batch, T, E, device=qkv.device, dtype=torch.float32)
     _run(lib.ia2p_causal_attn_small_f32, (qkv.data_ptr(), out.data_ptr(), batch, T, heads, _stream()), "causal_attn_small")
     return out
+
+
+def prior_trunk_workspace(rows, device):
+    """Zero-initialised workspace of ia2p_prior_trunk for `rows` = 2 * batch * T sequence rows (holds the grid-barrier state: allocate
+    once, reuse for every call)."""
+    n = _lib.load().ia2p_prior_trunk_workspace_bytes(rows)
+    return torch.zeros((n + 255) // 256 * 256, dtype=torch.uint8, device=device)
+
+
+def prior_trunk(seq, wpe, layers, lnf_g, lnf_b, heads, workspace, out=None, cache=None):
+    """x0 = ln_f(GPT2(inputs_embeds=seq))[:, -1] in ONE persistent kernel.  seq [B2, T, E] fp32; layers: per layer the 12 tensors
+    (wqkv, wo, wfc, wpr bf16 [out, in]; bqkv, bo, bfc, bpr, ln1 gamma, ln1 beta, ln2 gamma, ln2 beta fp32), see include/ia2p.h;
+    workspace from prior_trunk_workspace; cache: a dict that keeps the ctypes pointer table between calls."""
+    import ctypes
+    lib = _lib.load()
+    seq = _f32(seq, "seq")
+    B2, T, E = seq.shape
+    tab = None if cache is None else cache.get("table")
+    if tab is None:
+        flat = [t for L in layers for t in L]
+        for i, t in enumerate(flat):
+            _need(t, torch.bfloat16 if i % 12 < 4 else torch.float32, f"layers[{i // 12}][{i % 12}]")
+            assert t.is_contiguous()
+        tab = (ctypes.c_void_p * len(flat))(*[t.data_ptr() for t in flat])
+        if cache is not None:
+            cache["table"] = tab
+    if out is None:
+        out = torch.empty(B2, E, device=seq.device, dtype=torch.float32)
+    _run(lib.ia2p_prior_trunk, (seq.data_ptr(), wpe.data_ptr(), tab, len(layers), lnf_g.data_ptr(), lnf_b.data_ptr(), B2, T, E, heads,
+                                workspace.data_ptr(), workspace.numel(), out.data_ptr(), _stream()), "prior_trunk")
+    return out

@@ -90,6 +90,9 @@ class B200Prior(nn.Module):
             p.requires_grad_(False)
         self.noise_scheduler = B200DDPMScheduler()
         self.use_cuda_graph = use_cuda_graph
+        self.fused_trunk = True          # False: the per-op kernels (7 launches per layer), kept for A/B and for other widths
+        self.fused_trunk_max_rows = 32
+        self._trunk_ws = {}
         self._packed = None
         self._clip_hidden = None
         self._graphs = {}
@@ -119,6 +122,7 @@ class B200Prior(nn.Module):
         self._packed = None
         self._graphs.clear()
         self._seq_static.clear()
+        self._trunk_ws.clear()
         return r
 
     @property
@@ -193,8 +197,24 @@ class B200Prior(nn.Module):
         """GPT2Model(inputs_embeds=seq)["last_hidden_state"][:, -1] -> [2*bs, E] fp32."""
         P = self.prepare()
         B2, T, E = seq.shape
+        # the persistent kernel keeps the weights resident and walks 32-row chunks one after the other: it wins for one request
+        # (2 x 14 rows); batched requests spread their row chunks over more CTAs on the per-op kernels
+        if self.fused_trunk and E == 1024 and self.n_head == 16 and B2 * T <= self.fused_trunk_max_rows and len(P["layers"]) <= 30:
+            return self._trunk_last_fused(P, seq, B2, T)
         with ops.pdl():      # ~175 tiny dependent kernels: each one's prologue / weight prefetch overlaps its predecessor's tail
             return self._trunk_last_impl(P, seq, B2, T, E)
+
+    def _trunk_last_fused(self, P, seq, B2, T):
+        """ONE persistent cooperative kernel per step (csrc/smallm.cu prior_trunk_kernel) instead of 7 launches per layer."""
+        layers = P.get("_flat")
+        if layers is None:
+            layers = P["_flat"] = [(L["wqkv"], L["wo"], L["wfc"], L["wpr"], L["bqkv"], L["bo"], L["bfc"], L["bpr"],
+                                    L["ln1"][0], L["ln1"][1], L["ln2"][0], L["ln2"][1]) for L in P["layers"]]
+            P["_cache"] = {}
+        ws = self._trunk_ws.get(B2 * T)
+        if ws is None:
+            ws = self._trunk_ws[B2 * T] = ops.prior_trunk_workspace(B2 * T, seq.device)
+        return ops.prior_trunk(seq, P["wpe"], layers, P["lnf"][0], P["lnf"][1], self.n_head, ws, cache=P["_cache"])
 
     def _trunk_last_impl(self, P, seq, B2, T, E):
         h = ops.axpby(P["wpe"][:T].unsqueeze(0).expand(B2, T, E).contiguous(), seq, 1.0, 1.0).reshape(B2 * T, E)

@@ -246,3 +246,20 @@ def causal_attn_small(qkv, batch, T, heads, out=None):
     E = heads * 64
     q, k, v = [t.reshape(batch, T, heads, 64).transpose(1, 2) for t in qkv.reshape(batch, T, 3 * E).split(E, dim=2)]
     return F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(batch, T, E)
+
+
+def prior_trunk_workspace(rows, device):
+    return torch.zeros(256, dtype=torch.uint8, device=device)
+
+
+def prior_trunk(seq, wpe, layers, lnf_g, lnf_b, heads, workspace, out=None, cache=None):
+    """the persistent GPT-2 trunk kernel, restated op by op (fp32)"""
+    B2, T, E = seq.shape
+    h = (seq.float() + wpe[:T].float()[None]).reshape(B2 * T, E)
+    for wqkv, wo, wfc, wpr, bqkv, bo, bfc, bpr, g1, b1, g2, b2 in layers:
+        qkv = gemm_smallm(layernorm(h, g1, b1, 1e-5), wqkv, bias=bqkv)
+        att = causal_attn_small(qkv, B2, T, heads).reshape(B2 * T, E)
+        h = gemm_smallm(att, wo, bias=bo, residual=h)
+        f = gemm_smallm(layernorm(h, g2, b2, 1e-5), wfc, bias=bfc, act=ACT_GELU_NEW)
+        h = gemm_smallm(f, wpr, bias=bpr, residual=h)
+    return layernorm(h.reshape(B2, T, E)[:, -1].contiguous(), lnf_g, lnf_b, 1e-5)

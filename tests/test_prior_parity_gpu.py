@@ -82,3 +82,21 @@ def test_prior_batched_8_rows_match_the_per_sample_oracle(no_diffusion):
     with _RandnReplay(draws):                             # and the batched call is bit-reproducible
         y0, _ = b.generate_diffusion(3, 0, srcs, device="cpu", dtype=torch.float32, **kw)
     assert torch.equal(yb, y0)
+
+
+@pytest.mark.parametrize("bs,T", [(1, 14), (1, 11), (8, 14), (3, 7), (20, 14)])
+def test_fused_trunk_matches_per_op_kernels(bs, T):
+    """prior_trunk_kernel (one persistent cooperative kernel per step) against the per-op kernels it replaces (layernorm ->
+    gemm_smallm -> causal_attn_small -> ...), same weights, random sequences; repeated calls are bit-identical."""
+    _o, b = build(3, device="cuda", graph=False)
+    torch.manual_seed(bs * 100 + T)
+    seq = torch.randn(2 * bs, T, 1024, device="cuda")
+    b.fused_trunk, b.fused_trunk_max_rows = True, 1 << 20
+    y1 = b._trunk_last(seq).clone()
+    y2 = b._trunk_last(seq).clone()
+    assert torch.equal(y1, y2)
+    b.fused_trunk = False
+    y0 = b._trunk_last(seq)
+    rel = ((y1 - y0).norm() / y0.norm()).item()
+    print(f"fused trunk bs={bs} T={T}: rel-L2 vs per-op kernels {rel:.2e}")
+    assert y1.shape == (2 * bs, 1024) and rel < 1e-4

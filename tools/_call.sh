@@ -1,4 +1,7 @@
 set -u
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "flash or attn" 2>&1 | tail -5
-timeout 120 python tools/bench_fa.py 2>&1 | grep self-attn
+timeout 600 python -m pytest tests/test_prior_parity_gpu.py -x -q -m gpu 2>&1 | tail -3
+timeout 120 python tools/trace_prior.py 1 2>&1 | tail -14
+timeout 300 python bench.py --workload c1 --steps 3 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_c1_r02_fused.json
+python -c "
+import json; d=json.load(open('gpurun_out/bench_c1_r02_fused.json')); print('c1', d['value'], d['unit'], d['e2e']['value'], d['roofline']['trunk_graph_replay_us'])"
