@@ -249,6 +249,7 @@ struct PtParams {
   const float *seq, *wpe, *gf, *bf;
   float *h, *qkv, *att, *f, *out;
   unsigned long long* bar;   // arrival counter (zero-initialised once, then only ever incremented)
+  long long spin_limit;      // cycles a CTA may wait at a grid barrier before it traps (IA2P_SPIN_LIMIT_S seconds at 2 GHz; default 2 s)
   int n_layer, B2, T, rows, rows_pad;
 };
 
@@ -263,13 +264,13 @@ __device__ __forceinline__ unsigned long long pt_ld_acquire(const unsigned long 
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void pt_grid_sync(unsigned long long* bar, unsigned long long target) {
+__device__ __forceinline__ void pt_grid_sync(unsigned long long* bar, unsigned long long target, long long spin_limit) {
   __syncthreads();
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
     const long long t0 = clock64();
     while (pt_ld_acquire(bar) < target) {
-      if (clock64() - t0 > 4000000000LL) __trap();
+      if (clock64() - t0 > spin_limit) __trap();
     }
   }
   __syncthreads();
@@ -501,12 +502,12 @@ __global__ void __launch_bounds__(kPtThreads, 1) prior_trunk_kernel(const __grid
   for (int l = 0; l < p.n_layer; ++l) {
     const PtLayer& L = p.layer[l];
     PT_STAMP();
-    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
     pt_gemm_phase<3, 4, true>(p, wq, p.h, E, L.g1, L.b1, L.bqkv, IA2P_ACT_NONE, nullptr, p.qkv, 3 * E, 24 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
     pt_prefetch_w<1, 4>(wo, L.wo, 8 * c, E);
     PT_STAMP();
-    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
     // ---- P2: causal attention, one (batch row block b, head) item per CTA, one query per warp; lane j owns key j
     // (sequence b, head, query i) triples are dealt out one per WARP over the whole grid (32 heads-items x T queries: 448 warps' worth
@@ -544,23 +545,23 @@ __global__ void __launch_bounds__(kPtThreads, 1) prior_trunk_kernel(const __grid
       }
     }
     PT_STAMP();
-    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
     pt_gemm_phase<1, 4, false>(p, wo, p.att, E, nullptr, nullptr, L.bo, IA2P_ACT_NONE, p.h, p.h, E, 8 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
     pt_prefetch_w<4, 4>(wf, L.wfc, 32 * c, E);
     PT_STAMP();
-    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
     pt_gemm_phase<4, 4, true>(p, wf, p.h, E, L.g2, L.b2, L.bfc, IA2P_ACT_GELU_NEW, nullptr, p.f, 4 * E, 32 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
     pt_prefetch_w<1, 16>(wp, L.wpr, 8 * c, 4 * E);
     PT_STAMP();
-    pt_grid_sync(p.bar, bar_target += gridDim.x);
+    pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
     pt_gemm_phase<1, 16, false>(p, wp, p.f, 4 * E, nullptr, nullptr, L.bpr, IA2P_ACT_NONE, p.h, p.h, E, 8 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
     if (l + 1 < p.n_layer) pt_prefetch_w<3, 4>(wq, p.layer[l + 1].wqkv, 24 * c, E);
   }
   PT_STAMP();
-  pt_grid_sync(p.bar, bar_target += gridDim.x);
+  pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
   PT_STAMP();
   // ---- final: out[b] = ln_f(h[b, T - 1]); one CTA per row, two-pass statistics, 4 elements per thread
   for (int b = c; b < p.B2; b += gridDim.x) {
@@ -676,6 +677,15 @@ extern "C" int ia2p_prior_trunk(const float* seq, const float* wpe, const void* 
   p.att = f; f += rp * kPtE;
   p.f = f;
   p.seq = seq; p.wpe = wpe; p.gf = lnf_g; p.bf = lnf_b; p.out = out;
+  {
+    static long long limit = -1;                           // compute-sanitizer runs need minutes, not seconds
+    if (limit < 0) {
+      const char* e = getenv("IA2P_SPIN_LIMIT_S");
+      const double sec = (e != nullptr && atof(e) > 0.0) ? atof(e) : 2.0;
+      limit = (long long)(sec * 2.0e9);
+    }
+    p.spin_limit = limit;
+  }
   p.n_layer = n_layer; p.B2 = (int)B2; p.T = (int)T; p.rows = (int)rows; p.rows_pad = (int)rp;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(kPtCtas);

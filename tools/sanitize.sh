@@ -19,4 +19,15 @@ for t in $TOOLS; do
   echo "=== $t exit code $r"
   [ "$r" -ne 0 ] && rc=$r
 done
+# the persistent prior trunk (grid barriers: give its bounded waits minutes under the sanitizer) and the flash-attention edge cases
+for t in $TOOLS; do
+  echo "=== compute-sanitizer --tool $t (persistent prior trunk, flash attention incl. peaked rows)"
+  extra=""
+  [ "$t" = memcheck ] && extra="--leak-check no"
+  IA2P_SPIN_LIMIT_S=600 timeout 1500 compute-sanitizer --tool "$t" $extra --error-exitcode 7 --print-limit 20 \
+      python -m pytest tests/test_prior_parity_gpu.py tests/test_kernels_gpu.py -x -q -m gpu -k "(test_fused_trunk and (1-14 or 1-11 or 3-7)) or test_flash_self_attn" -p no:cacheprovider 2>&1 | grep -vE "^$" | tail -12
+  r=${PIPESTATUS[0]}
+  echo "=== $t exit code $r"
+  [ "$r" -ne 0 ] && rc=$r
+done
 exit $rc
