@@ -1,5 +1,9 @@
 set -u
-mkdir -p gpurun_out
-IA2P_SPIN_LIMIT_S=600 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 7 --print-limit 12 python -m pytest tests/test_prior_parity_gpu.py -x -q -m gpu -k "test_fused_trunk and (1-14 or 1-11 or 3-7)" -p no:cacheprovider > gpurun_out/race_prior3.log 2>&1
-echo "exit $?"
-grep -E "RACECHECK SUMMARY|passed|failed" gpurun_out/race_prior3.log
+for r in 1 2; do
+timeout 300 python tools/ab_step.py 1 64 60 2>&1 | grep ab_step
+IA2P_LIB_OVERRIDE=tools/libia2p_s9.so timeout 300 python tools/ab_step.py 1 64 60 2>&1 | grep ab_step
+done
+timeout 300 python tools/ab_step.py 1 128 40 2>&1 | grep ab_step
+IA2P_LIB_OVERRIDE=tools/libia2p_s9.so timeout 300 python tools/ab_step.py 1 128 40 2>&1 | grep ab_step
+timeout 300 python tools/ab_step.py 4 128 30 2>&1 | grep ab_step
+IA2P_LIB_OVERRIDE=tools/libia2p_s9.so timeout 300 python tools/ab_step.py 4 128 30 2>&1 | grep ab_step
