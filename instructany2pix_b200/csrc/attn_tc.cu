@@ -6,9 +6,9 @@
 //   softmax warps: S -> registers (chunk loads software-pipelined against the exp math), p = exp2(s*scale - m_ref) -> bf16
 //                  -> TMEM (64 columns, two keys per 32-bit cell: the A operand of MMA2 is read straight from TMEM)
 //   MMA2: O(TMEM, 64 cols fp32) += P(TMEM) V_j(smem, MN-major)               [M128 N64 K128]
-// O accumulates in TMEM across blocks; the running reference max m_ref is only raised (and O, l rescaled through
-// tcgen05.ld/st) when a row's block max exceeds it by more than 8 (log2 units), so the rescale path is rare and the
-// result is exact up to the common factor that cancels in O / l.  MMA1 of block j+1 is issued before MMA2 of block j, and
+// O accumulates in TMEM across blocks; the standing reference m_ref (first block: the maximum of its first 32 keys) is only raised
+// (and O, l rescaled through tcgen05.ld/st) when a row's block sum shows it is stale by more than 2^20, so the exact-max path is
+// rare and the result is exact up to the common factor that cancels in O / l.  MMA1 of block j+1 is issued before MMA2 of block j, and
 // two CTAs are co-resident per SM (80 KB smem, 256 TMEM columns each), so tensor work overlaps the softmax math.
 // (Round-1 history: P used to go through shared memory -- 16 swizzled 16-byte stores per thread + fence.proxy.async cost
 // 450 of the 2 700 cycles a key block took, tools/trace_attn.py; keeping P in TMEM removes that and 32 KB of smem.)
@@ -41,7 +41,7 @@ constexpr int kFaSmemBytes = kFaSmemTiles + 1024;  // barriers live in the align
 //    plus 8 cycles of the 4-lane SFU.  Per exponential: scale-subtract 1 + row sum 1 + pack 0.5..1 + (MUFU 1 | polynomial 7) slots,
 //    so ~6 cycles per exponential whatever the MUFU / polynomial split between 4/16 and 6/16 (sfubench "softmax mix" rows), i.e.
 //    >= 1 540 cycles per block of the CTA pair;
-//  * power: under this kernel the chip settles at ~1.54 GHz (1 kW cap), and that is what the variants converge to: one or two
+//  * power: under this kernel the chip draws the 1 kW cap (995 W, tools/fa_clocks.py) at ~1.54 GHz, and that is what the variants converge to: one or two
 //    threads per row (4 or 8 softmax warps), S in 64-key halves with their own barriers, a staggered start of the co-resident CTAs,
 //    truncating or rounding the bf16 pack, 4/16 .. 8/16 polynomial share all land at 840-900 TFLOP/s at 4 096 tokens and 600-660 at
 //    1 024 (round 1: 725 / 550; scalar FFMA with 1/4 polynomial: 829 / 588).
