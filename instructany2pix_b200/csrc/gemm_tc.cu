@@ -1236,6 +1236,11 @@ static int pick_block_n(int64_t N, bool geglu, int64_t m_tiles, int num_kb = 0) 
     const int v = atoi(e);
     if ((v == 64 || v == 128 || v == 160 || v == 256) && N % v == 0 && (!geglu || v % 64 == 0)) return v;
   }
+  if (N == 1280 && !geglu) {                             // experiments only: tile width of the N = 1280 problems (out-proj, to_q, FF-out)
+    static int bn1280 = -1;
+    if (bn1280 < 0) { const char* e = getenv("IA2P_GEMM_BN1280"); bn1280 = e ? atoi(e) : 0; }
+    if ((bn1280 == 128 || bn1280 == 160 || bn1280 == 64) && m_tiles * (N / bn1280) >= kMinTilesForWideBlock) return bn1280;
+  }
   const int cand[4] = {256, 160, 128, 64};
   int last = 0, first = 0;
   for (int i = 0; i < 4; ++i) {

@@ -1,9 +1,10 @@
 set -u
-for r in 1 2; do
-timeout 300 python tools/ab_step.py 1 64 60 2>&1 | grep ab_step
-IA2P_LIB_OVERRIDE=tools/libia2p_s9.so timeout 300 python tools/ab_step.py 1 64 60 2>&1 | grep ab_step
-done
-timeout 300 python tools/ab_step.py 1 128 40 2>&1 | grep ab_step
-IA2P_LIB_OVERRIDE=tools/libia2p_s9.so timeout 300 python tools/ab_step.py 1 128 40 2>&1 | grep ab_step
-timeout 300 python tools/ab_step.py 4 128 30 2>&1 | grep ab_step
-IA2P_LIB_OVERRIDE=tools/libia2p_s9.so timeout 300 python tools/ab_step.py 4 128 30 2>&1 | grep ab_step
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep smoke
+timeout 900 python bench.py 2>/dev/null | tail -1 > gpurun_out/bench_c3_r02_final2.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_c3_r02_final2.json'))
+print('c3', d['value'], d['unet_step_ms'], d['unet_tensor_frac'], 'e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], d['clocks'], 'cpu', d['cpu_baseline']['value'], 'launches', d['gpu_launches'])
+PY
