@@ -265,6 +265,7 @@ __device__ __forceinline__ unsigned long long pt_ld_acquire(const unsigned long 
   return v;
 }
 __device__ __forceinline__ void pt_grid_sync(unsigned long long* bar, unsigned long long target, long long spin_limit) {
+  asm volatile("fence.proxy.async.global;" ::: "memory");     // this thread's global writes are read through the async proxy (bulk copies) next
   __syncthreads();
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
@@ -278,8 +279,11 @@ __device__ __forceinline__ void pt_grid_sync(unsigned long long* bar, unsigned l
 #ifdef IA2P_TC_TRACE
 __device__ unsigned long long* g_pt_trace = nullptr;           // debug build: globaltimer stamps of CTA 0, one per phase boundary
 #define PT_STAMP() do { if (g_pt_trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_pt_trace[pt_n++] = gtime_ns(); } while (0)
+__device__ unsigned long long* g_pt_fine = nullptr;            // debug build: stamps INSIDE the GEMM phases of CTA 0 (thread 0), 6 per phase call
+#define PT_FINE() do { if (g_pt_fine != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_pt_fine[fine_base + fine_i++] = gtime_ns(); } while (0)
 #else
 #define PT_STAMP()
+#define PT_FINE()
 #endif
 
 template <int NT, int NS>
@@ -298,11 +302,27 @@ __device__ __forceinline__ void cp_async_cg16(uint32_t dst, const void* src, boo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// 1-D bulk copy global -> shared through the TMA engine (no tensor map), completing `bytes` on an mbarrier.  16-byte aligned ends.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // A staging: a ring of kPtRing slots; a slot holds two 32-wide k-steps of every warp's k-slice for a 32-row chunk: [8 warps][32 rows]
 // [64 fp32 + 4 pad] (272-byte rows: the 16-byte fragment reads of a quarter warp fall into different bank groups).
 constexpr int kPtRing = 3, kPtRowB = 272, kPtWarpB = 32 * kPtRowB, kPtSlotB = 8 * kPtWarpB;
+// The trunk's activations that feed a GEMM phase (h, att, f) live in global memory ALREADY in that staging order -- [32-row chunk]
+// [round][warp k-slice][row][64 fp32 + 4 pad] -- so a whole ring slot is one contiguous 69 632-byte block: a phase stages its A
+// operand with ONE bulk copy (TMA engine) per round instead of 16 cp.async per lane (LSU: ~1.2 us of issue + 1.4 us of landing per
+// 128 KB with all 128 CTAs pulling the same rows; 256-byte bulk copies per row were no faster).  Rows past the sequence count are
+// never written and stay zero from the workspace's one-time initialisation.  K = columns of the buffer (1024 | 4096).
+__device__ __forceinline__ size_t pt_idx(int m, int k, int K) {
+  const int kw = K >> 3, w = k / kw, kr = k - w * kw;            // warp k-slice, offset inside it
+  return ((((size_t)(m >> 5) * (kw >> 6) + (kr >> 6)) * 8 + w) * 32 + (m & 31)) * (kPtRowB / 4) + (kr & 63);
+}
+__host__ __device__ constexpr long long pt_floats(long long rows_pad, long long K) { return rows_pad * K / 64 * (kPtRowB / 4); }
 
 // One GEMM phase of this CTA: out[rows, n0 .. n0 + 8 NT) over K = 256 NS with the weights already in registers.  A (written by
 // other SMs in the previous phase) comes through L2 by cp.async.cg, every load of up to three slots in flight at once: one L2
@@ -312,23 +332,32 @@ template <int NT, int NS, bool LN>
 __device__ __forceinline__ void pt_gemm_phase(const PtParams& p, const uint4 (&wv)[NT * NS], const float* __restrict__ A, int lda,
                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                               const float* __restrict__ bias, int act, const float* residual, float* out, int ldo,
-                                              int n0, uint8_t* s_ring, float* s_mean, float* s_rstd, float* s_part, float* s_gb) {
-  constexpr int K = NS * 256, NC = NT * 8, NR = NS / 2;          // NR rounds of two k-steps
+                                              bool out_tiled,
+                                              int n0, uint8_t* s_ring, float* s_mean, float* s_rstd, float* s_part, float* s_gb, uint32_t bars, uint32_t& ring_par,
+                                              int fine_base) {
+  constexpr int K = NS * 256, NC = NT * 8, NR = NS / 2;
+  (void)lda; (void)K;
+  int fine_i = 0;
+  (void)fine_base; (void)fine_i;          // NR rounds of two k-steps
   static_assert(!LN || NR <= kPtRing, "LayerNorm needs the whole row chunk resident");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int k_lo = warp * (K >> 3);
   const uint32_t ring = smem_u32(s_ring);
   float* s_red = reinterpret_cast<float*>(s_ring);               // the reduction buffer reuses slot 0 once the MMAs are done
   for (int m0 = 0; m0 < p.rows; m0 += 32) {
-    auto issue = [&](int round) {                                // this warp's 32 rows x 64 k of round `round`: 16 x 16 B per lane
-      const uint32_t dst = ring + (uint32_t)((round % kPtRing) * kPtSlotB + warp * kPtWarpB);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int q = i * 32 + lane, row = q >> 4, c4 = q & 15;
-        const bool ok = m0 + row < p.rows;
-        cp_async_cg16(dst + (uint32_t)(row * kPtRowB + c4 * 16), A + (long long)(ok ? m0 + row : 0) * lda + k_lo + round * 64 + c4 * 4, ok);
+    // round `round` of this row chunk = one contiguous slot image in global memory: ONE bulk copy, issued by thread 0
+    auto issue = [&](int round) {
+      if (threadIdx.x == 0) {
+        const int slot = round % kPtRing;
+        const uint32_t bar = bars + (uint32_t)slot * 8u;
+        mbar_arrive_expect_tx(bar, (uint32_t)kPtSlotB);
+        bulk_g2s(ring + (uint32_t)(slot * kPtSlotB), A + ((size_t)(m0 >> 5) * NR + round) * (kPtSlotB / 4), (uint32_t)kPtSlotB, bar);
       }
-      cp_async_commit();
+    };
+    auto wait_round = [&](int round) {                           // every thread polls: the data is then visible to each of them
+      const int slot = round % kPtRing;
+      mbar_wait(bars + (uint32_t)slot * 8u, (ring_par >> slot) & 1u);
+      ring_par ^= 1u << slot;
     };
     if (LN && m0 == 0) {                                         // gamma | beta of the phase: 2 x 4 KB, same cp.async group as round 0
 #pragma unroll
@@ -338,15 +367,20 @@ __device__ __forceinline__ void pt_gemm_phase(const PtParams& p, const uint4 (&w
       }
     }
     // NT == 1 phases add the residual: its one value per thread is requested now, not after the reduction
+    PT_FINE();
     float res_pref = 0.f;
     if (NT == 1 && residual != nullptr && m0 + (threadIdx.x >> 3) < p.rows)
-      res_pref = __ldcg(residual + (long long)(m0 + (threadIdx.x >> 3)) * ldo + n0 + (threadIdx.x & 7));
+      res_pref = __ldcg(residual + pt_idx(m0 + (threadIdx.x >> 3), n0 + (threadIdx.x & 7), ldo));   // residual = h: always tiled
 #pragma unroll
     for (int r = 0; r < kPtRing; ++r)
       if (r < NR) issue(r);
+    PT_FINE();
     if (LN) {
-      cp_async_wait<0>();
+      if (m0 == 0) cp_async_wait<0>();                           // gamma / beta
+      wait_round(0);
+      wait_round(1);
       __syncthreads();
+      PT_FINE();
       // thread (warp w, lane r): the 128 values of row r staged by warp w (two slots) -- neighbouring lanes read neighbouring rows
       // (272-byte pitch: conflict-free 16-byte reads; one thread per (row, region) pair with 8 lanes per row was an 8-way bank
       // conflict on every load and cost 7 us per phase); the 8 regions' partials meet in shared memory, summed in region order
@@ -386,6 +420,8 @@ __device__ __forceinline__ void pt_gemm_phase(const PtParams& p, const uint4 (&w
       }
       __syncthreads();
     }
+    if (!LN) PT_FINE();
+    PT_FINE();
     float acc[2][NT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -399,12 +435,7 @@ __device__ __forceinline__ void pt_gemm_phase(const PtParams& p, const uint4 (&w
     }
 #pragma unroll
     for (int round = 0; round < NR; ++round) {
-      if (!LN) {                                                 // rounds complete in order; later ones stay in flight
-        if (NR - 1 - round >= 2) cp_async_wait<2>();
-        else if (NR - 1 - round == 1) cp_async_wait<1>();
-        else cp_async_wait<0>();
-        __syncwarp();
-      }
+      if (!LN) wait_round(round);                                // later rounds stay in flight
       const uint8_t* slot = s_ring + (round % kPtRing) * kPtSlotB + warp * kPtWarpB;
 #pragma unroll
       for (int s2 = 0; s2 < 2; ++s2) {
@@ -444,14 +475,16 @@ __device__ __forceinline__ void pt_gemm_phase(const PtParams& p, const uint4 (&w
           }
         }
       }
-      if (round + kPtRing < NR) {                                // refill this slot (the warp's own region: a warp-level hand-over)
-        __syncwarp();
+      if (round + kPtRing < NR) {                                // refill this slot once every warp has consumed it
+        __syncthreads();
         issue(round + kPtRing);
       }
     }
     // the 8 warps' k-slice partials -> shared memory [warp][32 rows][NC + 1] (over slot 0), summed in warp order
     constexpr int PP = NC + 1;
+    PT_FINE();
     __syncthreads();                                             // every warp is done reading the ring
+    PT_FINE();
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -472,11 +505,13 @@ __device__ __forceinline__ void pt_gemm_phase(const PtParams& p, const uint4 (&w
       if (m < p.rows) {
         v += __ldg(bias + n);
         v = apply_act(v, act);
-        if (residual != nullptr) v += (NT == 1) ? res_pref : __ldcg(residual + (long long)m * ldo + n);
-        out[(long long)m * ldo + n] = v;
+        if (residual != nullptr) v += (NT == 1) ? res_pref : __ldcg(residual + pt_idx(m, n, ldo));
+        out[out_tiled ? pt_idx(m, n, ldo) : (size_t)m * ldo + n] = v;
       }
     }
+    fence_proxy_async();                                         // this thread's generic accesses of the ring, before the next bulk copies land in it
     __syncthreads();                                             // s_red (slot 0) / s_mean are reused by the next row chunk
+    PT_FINE();
   }
 }
 
@@ -484,6 +519,14 @@ __global__ void __launch_bounds__(kPtThreads, 1) prior_trunk_kernel(const __grid
   extern __shared__ __align__(16) uint8_t s_ring[];             // kPtRing x kPtSlotB
   __shared__ float s_mean[32], s_rstd[32], s_part[8 * 32];
   __shared__ __align__(16) float s_gb[2 * kPtE];
+  __shared__ __align__(8) unsigned long long s_bars[kPtRing];       // one mbarrier per ring slot
+  const uint32_t bars = smem_u32(s_bars);
+  uint32_t ring_par = 0;                                         // phase parity per slot (every thread keeps its copy)
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPtRing; ++i) mbar_init(bars + 8u * i, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
   const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int E = kPtE, T = p.T;
   uint4 wq[12], wo[4], wf[16], wp[16];
@@ -497,22 +540,22 @@ __global__ void __launch_bounds__(kPtThreads, 1) prior_trunk_kernel(const __grid
   for (int m0 = 0; m0 < p.rows; m0 += 32) {
     const int row = m0 + (threadIdx.x >> 3), n = 8 * c + (threadIdx.x & 7);
     const bool ok = row < p.rows;
-    if (ok) p.h[(long long)row * E + n] = __ldg(p.seq + (long long)row * E + n) + __ldg(p.wpe + (long long)(row % T) * E + n);
+    if (ok) p.h[pt_idx(row, n, E)] = __ldg(p.seq + (long long)row * E + n) + __ldg(p.wpe + (long long)(row % T) * E + n);
   }
   for (int l = 0; l < p.n_layer; ++l) {
     const PtLayer& L = p.layer[l];
     PT_STAMP();
     pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
-    pt_gemm_phase<3, 4, true>(p, wq, p.h, E, L.g1, L.b1, L.bqkv, IA2P_ACT_NONE, nullptr, p.qkv, 3 * E, 24 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
+    pt_gemm_phase<3, 4, true>(p, wq, p.h, E, L.g1, L.b1, L.bqkv, IA2P_ACT_NONE, nullptr, p.qkv, 3 * E, false, 24 * c, s_ring, s_mean, s_rstd, s_part, s_gb, bars, ring_par, (l * 4 + 0) * 8);
     pt_prefetch_w<1, 4>(wo, L.wo, 8 * c, E);
     PT_STAMP();
     pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
     // ---- P2: causal attention, one (batch row block b, head) item per CTA, one query per warp; lane j owns key j
-    // (sequence b, head, query i) triples are dealt out one per WARP over the whole grid (32 heads-items x T queries: 448 warps' worth
-    // of work at batch 1; one item per CTA left 96 of the 128 CTAs idle and the phase 6 us long)
-    for (int wi = c * 8 + warp; wi < p.B2 * 16 * T; wi += gridDim.x * 8) {
+    // (sequence b, head, query i) triples are dealt out one per WARP over the whole grid, warp-major (32 heads-items x T queries: 448
+    // warps' worth of work at batch 1 = 3.5 per CTA; one item per CTA left 96 of the 128 CTAs idle and the phase 6 us long)
+    for (int wi = warp * (int)gridDim.x + c; wi < p.B2 * 16 * T; wi += gridDim.x * 8) {   // warp-major: every SM gets its share
       {
         const int item = wi / T, i = wi - item * T;
         const int b = item >> 4, hd = item & 15;
@@ -541,23 +584,23 @@ __global__ void __launch_bounds__(kPtThreads, 1) prior_trunk_kernel(const __grid
             o1 += pj * vv.y;
           }
         }
-        *reinterpret_cast<float2*>(p.att + ((long long)b * T + i) * E + hd * 64 + 2 * lane) = make_float2(o0 / sum, o1 / sum);
+        *reinterpret_cast<float2*>(p.att + pt_idx(b * T + i, hd * 64 + 2 * lane, E)) = make_float2(o0 / sum, o1 / sum);
       }
     }
     PT_STAMP();
     pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
-    pt_gemm_phase<1, 4, false>(p, wo, p.att, E, nullptr, nullptr, L.bo, IA2P_ACT_NONE, p.h, p.h, E, 8 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
+    pt_gemm_phase<1, 4, false>(p, wo, p.att, E, nullptr, nullptr, L.bo, IA2P_ACT_NONE, p.h, p.h, E, true, 8 * c, s_ring, s_mean, s_rstd, s_part, s_gb, bars, ring_par, (l * 4 + 1) * 8);
     pt_prefetch_w<4, 4>(wf, L.wfc, 32 * c, E);
     PT_STAMP();
     pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
-    pt_gemm_phase<4, 4, true>(p, wf, p.h, E, L.g2, L.b2, L.bfc, IA2P_ACT_GELU_NEW, nullptr, p.f, 4 * E, 32 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
+    pt_gemm_phase<4, 4, true>(p, wf, p.h, E, L.g2, L.b2, L.bfc, IA2P_ACT_GELU_NEW, nullptr, p.f, 4 * E, true, 32 * c, s_ring, s_mean, s_rstd, s_part, s_gb, bars, ring_par, (l * 4 + 2) * 8);
     pt_prefetch_w<1, 16>(wp, L.wpr, 8 * c, 4 * E);
     PT_STAMP();
     pt_grid_sync(p.bar, bar_target += gridDim.x, p.spin_limit);
     PT_STAMP();
-    pt_gemm_phase<1, 16, false>(p, wp, p.f, 4 * E, nullptr, nullptr, L.bpr, IA2P_ACT_NONE, p.h, p.h, E, 8 * c, s_ring, s_mean, s_rstd, s_part, s_gb);
+    pt_gemm_phase<1, 16, false>(p, wp, p.f, 4 * E, nullptr, nullptr, L.bpr, IA2P_ACT_NONE, p.h, p.h, E, true, 8 * c, s_ring, s_mean, s_rstd, s_part, s_gb, bars, ring_par, (l * 4 + 3) * 8);
     if (l + 1 < p.n_layer) pt_prefetch_w<3, 4>(wq, p.layer[l + 1].wqkv, 24 * c, E);
   }
   PT_STAMP();
@@ -565,7 +608,7 @@ __global__ void __launch_bounds__(kPtThreads, 1) prior_trunk_kernel(const __grid
   PT_STAMP();
   // ---- final: out[b] = ln_f(h[b, T - 1]); one CTA per row, two-pass statistics, 4 elements per thread
   for (int b = c; b < p.B2; b += gridDim.x) {
-    const float4 x = __ldcg(reinterpret_cast<const float4*>(p.h + ((long long)b * T + T - 1) * E) + threadIdx.x);
+    const float4 x = __ldcg(reinterpret_cast<const float4*>(p.h + pt_idx(b * T + T - 1, 4 * (int)threadIdx.x, E)));
     float s = warp_sum(x.x + x.y + x.z + x.w);
     if (lane == 0) s_mean[warp] = s;
     __syncthreads();
@@ -643,7 +686,7 @@ extern "C" int ia2p_causal_attn_small_f32(const float* qkv, float* out, int64_t 
 
 extern "C" int64_t ia2p_prior_trunk_workspace_bytes(int64_t rows) {
   const int64_t rp = (rows + 31) / 32 * 32;
-  return 256 + rp * kPtE * 4 * (1 + 3 + 1 + 4);
+  return 256 + 4 * (2 * pt_floats(rp, kPtE) + pt_floats(rp, 4 * kPtE) + rp * 3 * kPtE);   // h, att, f (staging order, padded) + qkv
 }
 
 extern "C" int ia2p_prior_trunk(const float* seq, const float* wpe, const void* const* layer_ptrs, int n_layer, const float* lnf_g,
@@ -672,10 +715,10 @@ extern "C" int ia2p_prior_trunk(const float* seq, const float* wpe, const void* 
   char* ws = static_cast<char*>(workspace);
   p.bar = reinterpret_cast<unsigned long long*>(ws);
   float* f = reinterpret_cast<float*>(ws + 256);
-  p.h = f; f += rp * kPtE;
-  p.qkv = f; f += rp * kPtE * 3;
-  p.att = f; f += rp * kPtE;
-  p.f = f;
+  p.h = f; f += pt_floats(rp, kPtE);
+  p.att = f; f += pt_floats(rp, kPtE);
+  p.f = f; f += pt_floats(rp, 4 * kPtE);
+  p.qkv = f;
   p.seq = seq; p.wpe = wpe; p.gf = lnf_g; p.bf = lnf_b; p.out = out;
   {
     static long long limit = -1;                           // compute-sanitizer runs need minutes, not seconds
@@ -704,6 +747,10 @@ extern "C" int ia2p_prior_trunk(const float* seq, const float* wpe, const void* 
 }
 
 #ifdef IA2P_TC_TRACE
+extern "C" int ia2p_debug_set_pt_fine(void* dev_buffer) {      // debug build only; resets the stamp counter
+  unsigned long long* q = static_cast<unsigned long long*>(dev_buffer);
+  return (int)cudaMemcpyToSymbol(ia2p::g_pt_fine, &q, sizeof(q));
+}
 extern "C" int ia2p_debug_set_pt_trace(void* dev_buffer) {     // debug build only; not part of include/ia2p.h
   unsigned long long* q = static_cast<unsigned long long*>(dev_buffer);
   return (int)cudaMemcpyToSymbol(ia2p::g_pt_trace, &q, sizeof(q));

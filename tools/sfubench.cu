@@ -64,7 +64,46 @@ static void run(const char* what) {
   cudaFree(out); cudaFree(sink);
 }
 
+// legacy warp-level tensor-core path: mma.sync.m16n8k16 bf16 (what gemm_smallm_kernel / prior_trunk_kernel use): NCH independent accumulator chains
+template <int NCH>
+__global__ void hmma_kernel(long long* out, float* sink, int iters) {
+  float c[NCH][4];
+  for (int i = 0; i < NCH; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+  const unsigned a0 = 0x3f803f80u + threadIdx.x, a1 = 0x3f003f00u, a2 = 0x3e803e80u, a3 = 0x3f803f00u, b0 = 0x3f803f80u, b1 = 0x3f003f80u;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+  for (int i = 0; i < NCH; ++i) acc += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (acc == 123.456f) sink[0] = acc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+}
+template <int NCH>
+static void run_hmma() {
+  long long* out; float* sink;
+  cudaMalloc(&out, 8); cudaMalloc(&sink, 4);
+  const int iters = 2000;
+  printf("mma.sync m16n8k16 bf16, %d independent accumulators per warp:", NCH);
+  for (int wps : {1, 2, 4}) {
+    hmma_kernel<NCH><<<148, 128 * wps>>>(out, sink, iters);
+    long long c = 0;
+    cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
+    printf("  %d w/SMSP: %6.1f clk per HMMA per sub-partition", wps, (double)c / iters / NCH / wps);
+  }
+  printf("\n");
+  cudaFree(out); cudaFree(sink);
+}
+
 int main() {
+  run_hmma<1>();
+  run_hmma<2>();
+  run_hmma<8>();
   printf("cycles per loop iteration (all resident warps run the same iteration concurrently)\n");
   run<8, 0, 0, 0, 0, 0>("8 MUFU.EX2");
   run<0, 8, 0, 0, 0, 0>("8 FFMA2");

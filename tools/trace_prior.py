@@ -17,6 +17,7 @@ from instructany2pix_b200.prior import B200Prior  # noqa: E402
 
 lib = _lib.load()
 lib.ia2p_debug_set_pt_trace.argtypes = [ctypes.c_void_p]
+lib.ia2p_debug_set_pt_fine.argtypes = [ctypes.c_void_p]
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 torch.set_grad_enabled(False)
 torch.manual_seed(0)
@@ -29,6 +30,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = torch.zeros(4096, dtype=torch.int64, device="cuda")
 lib.ia2p_debug_set_pt_trace(buf.data_ptr())
+fine = torch.zeros(8192, dtype=torch.int64, device="cuda")
+lib.ia2p_debug_set_pt_fine(fine.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 pr._trunk_last(seq)
@@ -59,3 +62,20 @@ print(f"prior trunk bs={bs}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us (events),
 for nm, a in zip(names, acc):
     print(f"  {nm:32s} {a / (L - 1) / 1e3:6.2f}")
 print(f"  sum per layer {sum(acc) / (L - 1) / 1e3:6.2f}")
+# inside the GEMM phases (8 stamps per phase call at <= 32 rows): start | loads issued | (LN: rows landed) | statistics done | MMA loop done |
+# all warps done | partials in smem ... | epilogue done
+f = fine.cpu().tolist()
+per = 8
+pn = ["P1 LN1+QKV", "P3 O-proj", "P4 LN2+FC", "P5 FC-out"]
+seg = ["issue cp.async", "wait rows (LN) / -", "LN statistics / -", "fragments + MMA", "wait other warps", "reduce + epilogue"]
+tot = [[0.0] * 7 for _ in range(4)]
+for l in range(1, L):
+    for ph in range(4):
+        s0 = (l * 4 + ph) * per
+        st = f[s0:s0 + per]
+        for i in range(7):
+            tot[ph][i] += st[i + 1] - st[i]
+print("inside the GEMM phases (us, CTA 0 thread 0, mean over layers):")
+for ph in range(4):
+    t7 = [x / (L - 1) / 1e3 for x in tot[ph]]
+    print(f"  {pn[ph]:12s} issue {t7[0]:5.2f} | rows landed {t7[1]:5.2f} | statistics {t7[2]:5.2f} | (stamp) {t7[3]:5.2f} | fragments + MMA {t7[4]:5.2f} | wait warps {t7[5]:5.2f} | reduce + epilogue {t7[6]:5.2f}")
