@@ -575,13 +575,20 @@ __global__ void __launch_bounds__(kPtThreads, 1) prior_trunk_kernel(const __grid
         const float sum = warp_sum(pr);
         float o0 = 0.f, o1 = 0.f;
         const float* vb = base + 2 * E + 2 * lane;
+        // all value rows are requested at once, 16 keys at a time (inside `if (j <= i)` blocks the compiler kept each load next to its
+        // use: one L2 round trip per key, 4 us for the last queries of a sequence -- the barrier after this phase waited for them)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j <= i) {                                          // warp-uniform; unrolled: the value loads are independent
-            const float pj = __shfl_sync(0xffffffffu, pr, j);
-            const float2 vv = __ldcg(reinterpret_cast<const float2*>(vb + (long long)j * 3 * E));
-            o0 += pj * vv.x;
-            o1 += pj * vv.y;
+        for (int j0 = 0; j0 < 32; j0 += 16) {
+          if (j0 <= i) {                                         // warp-uniform
+            float2 vv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vv[j] = __ldcg(reinterpret_cast<const float2*>(vb + (long long)((j0 + j <= i) ? j0 + j : i) * 3 * E));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float pj = (j0 + j <= i) ? __shfl_sync(0xffffffffu, pr, j0 + j) : 0.f;
+              o0 += pj * vv[j].x;
+              o1 += pj * vv[j].y;
+            }
           }
         }
         *reinterpret_cast<float2*>(p.att + pt_idx(b * T + i, hd * 64 + 2 * lane, E)) = make_float2(o0 / sum, o1 / sum);
