@@ -249,7 +249,7 @@ struct PtParams {
   const float *seq, *wpe, *gf, *bf;
   float *h, *qkv, *att, *f, *out;
   unsigned long long* bar;   // arrival counter (zero-initialised once, then only ever incremented)
-  long long spin_limit;      // cycles a CTA may wait at a grid barrier before it traps (IA2P_SPIN_LIMIT_S seconds at 2 GHz; default 2 s)
+  long long spin_limit;      // cycles a CTA may wait at a grid barrier before it traps (IA2P_SPIN_LIMIT_S seconds at 2 GHz; default 10 s)
   int n_layer, B2, T, rows, rows_pad;
 };
 
@@ -731,7 +731,7 @@ extern "C" int ia2p_prior_trunk(const float* seq, const float* wpe, const void* 
     static long long limit = -1;                           // compute-sanitizer runs need minutes, not seconds
     if (limit < 0) {
       const char* e = getenv("IA2P_SPIN_LIMIT_S");
-      const double sec = (e != nullptr && atof(e) > 0.0) ? atof(e) : 2.0;
+      const double sec = (e != nullptr && atof(e) > 0.0) ? atof(e) : 10.0;
       limit = (long long)(sec * 2.0e9);
     }
     p.spin_limit = limit;
