@@ -225,7 +225,7 @@ __global__ void causal_attn_small_kernel(const float* __restrict__ qkv, float* _
 // together and meet at a grid-wide barrier between phases:
 //   prologue  h = seq + wpe
 //   P1  qkv = LN1(h) Wqkv^T + b          CTA c: 24 of the 3 072 columns, K = 1 024 over the 8 warps
-//   P2  att = causal softmax(q k^T / 8) v                    one (sequence, head) item per CTA
+//   P2  att = causal softmax(q k^T / 8) v                    one (sequence, head, query) triple per WARP, dealt out over the whole grid
 //   P3  h += att Wo^T + b                CTA c: 8 of 1 024 columns
 //   P4  f = gelu_new(LN2(h) Wfc^T + b)   CTA c: 32 of 4 096 columns
 //   P5  h += f Wpr^T + b                 CTA c: 8 of 1 024 columns, K = 4 096
@@ -233,11 +233,13 @@ __global__ void causal_attn_small_kernel(const float* __restrict__ qkv, float* _
 // Every CTA owns whole output COLUMNS over the full K, so there is no split-K exchange between CTAs: the 8 warps of a CTA split K,
 // their partial tiles are summed through shared memory in warp order (bit-reproducible).  Weights are STATIONARY per phase: a
 // lane's 16-byte weight loads of the next phase are issued BEFORE the barrier that ends the current one, so the HBM latency hides
-// behind the barrier.  A (fp32, 32 rows at a time, written by other SMs in the previous phase) is staged through L2 by cp.async.cg
-// with every load of a phase in flight at once, and turned into hi + lo bf16 mma.sync fragments on the way to the tensor cores;
-// LayerNorm is folded into that (exact two-pass row statistics over the staged rows, gamma / beta per k).  Row counts above 32
-// (batched requests) reuse the resident weights.  First version (A fragments loaded straight from L2 per k-step, row statistics
-// from per-CTA partial sums, value loads of the attention in a run-time loop): 1 282 us per step -- one L2 round trip per k-step.
+// behind the barrier.  A (fp32, 32 rows at a time, written by other SMs in the previous phase) lives in HBM in the kernel's own
+// staging order (pt_idx), so a ring slot is one contiguous block that ONE bulk (TMA) copy brings in; it is turned into hi + lo bf16
+// mma.sync fragments on the way to the tensor cores; LayerNorm is folded into that (exact two-pass row statistics over the staged
+// rows, gamma / beta per k).  Row counts above 32 (batched requests) reuse the resident weights, chunk after chunk -- the host keeps
+// those on the per-op kernels.  History (profiles/trace_prior_r02.log): A fragments straight from L2 per k-step 1 282 us per step;
+// cp.async staging with a bank-conflicted statistics pass 1 469; conflict-free + packed hi / lo split 1 154; staging order in HBM +
+// bulk copies 935; the attention's value rows requested at once 847 (per-op kernels: 1 477).
 constexpr int kPtCtas = 128, kPtThreads = 256, kPtMaxLayers = 30, kPtE = 1024;
 
 struct PtLayer {
