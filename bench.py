@@ -56,6 +56,14 @@ def peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
 
 
+def ncu_traffic_prior():
+    """DRAM bytes (read + write) of ONE prior_trunk_kernel launch from the committed `ncu --set full` capture (not measured live)."""
+    p = os.path.join(ROOT, "profiles", "prior_trunk_traffic_r02.json")
+    if os.path.exists(p):
+        return json.load(open(p))["dram_bytes_per_launch"]
+    return None
+
+
 def ncu_traffic():
     """DRAM bytes (read + write) per tc_gemm_kernel launch, averaged over the 480 launches of one UNet step, from the committed
     ncu capture (profiles/gemm_traffic_r02.json; not measured live -- a run under ncu is never a bench value)."""
@@ -534,7 +542,7 @@ def bench_prior(args, wl, dev, rank, world, local):
                gpu_launches=int(launches_eager + (args.steps * PRIOR_STEPS * per_step_kernels if prior.use_cuda_graph else 0)),
                roofline=dict(kernel=("prior_trunk_kernel (the whole GPT-2-medium trunk of a step as one persistent cooperative kernel, 128 CTAs, grid "
                                      "barriers between phases; " if fused else "gemm_smallm_kernel (GPT-2-medium trunk, ") + "M = 2 CFG rows x 14 tokens)", bound="hbm", achieved=ach, peak=pk["hbm"],
-                             unit="GB/s", frac=ach / pk["hbm"], traffic=None, peak_source=pk["src"] + " hbm_gbs",
+                             unit="GB/s", frac=ach / pk["hbm"], traffic=ncu_traffic_prior() if fused else None, peak_source=pk["src"] + " hbm_gbs",
                              algorithmic_bytes_per_step=wbytes, launches_per_step=per_step_kernels, eager_trunk_gemm_ms_per_step=trunk_ms,
                              trunk_graph_replay_us=trunk_us, trunk_graph_gbs=None if not trunk_us else wbytes / (trunk_us * 1e-6) / 1e9,
                              floor_us=wbytes / (pk["hbm"] * 1e9) * 1e6))
