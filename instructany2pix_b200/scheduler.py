@@ -176,3 +176,74 @@ class B200DDPMScheduler(_SchedulerBase):
         c_x = math.sqrt(cur_a) * (1.0 - a_p) / (1.0 - a_t)
         sigma = math.sqrt(max((1.0 - a_p) / (1.0 - a_t) * cur_b, 1e-20)) if t > 0 else 0.0
         return dict(sqrt_a=math.sqrt(a_t), sqrt_1ma=math.sqrt(1.0 - a_t), c_x0=c_x0, c_x=c_x, sigma=sigma)
+
+class B200LCMScheduler(B200DDIMScheduler):
+    """[3P] ``LCMScheduler`` (latent consistency models): the reference's 4-step ``ipa_lcm`` mode (``serve.py:90``,
+    ``sdxl_img2img_pipeline.py:91-104``: ``LCMScheduler.from_config(pipeline.scheduler.config)`` + the LCM LoRA; commented out in
+    the shipped ``pipeline.py:102-103``).  Restated from the published diffusers 0.26 algorithm (parity unpinned:
+    diffusers is not in this image): timesteps = every ``len / n``-th of the ``original_inference_steps`` training-schedule
+    points, x0 prediction, consistency boundary scalings c_skip / c_out with sigma_data 0.5, and -- on every step but the last --
+    re-noising to the next timestep.  Like DDIM the deterministic part is linear in (x, eps), so ``cfg_step`` is the same fused
+    CFG + update kernel with other host-side fp64 coefficients, followed by one axpby with fresh noise (drawn on the latents'
+    device from ``self.generator`` / the global RNG, like ``randn_tensor`` in the original)."""
+
+    def __init__(self, original_inference_steps=50, timestep_scaling=10.0, **kw):
+        super().__init__(**kw)
+        self.config.original_inference_steps = int(original_inference_steps)
+        self.config.timestep_scaling = float(timestep_scaling)
+        self.generator = None
+
+    def set_timesteps(self, num_inference_steps, device=None, original_inference_steps=None, strength=1.0):
+        self.num_inference_steps = int(num_inference_steps)
+        orig = int(original_inference_steps or self.config.original_inference_steps)
+        k = self._cfg["num_train_timesteps"] // orig
+        origin = (np.arange(1, int(orig * strength) + 1) * k - 1)[::-1].copy()
+        if self.num_inference_steps > len(origin):
+            raise ValueError(f"num_inference_steps {num_inference_steps} exceeds the {len(origin)} points of the LCM training schedule")
+        idx = np.floor(np.linspace(0, len(origin), num=self.num_inference_steps, endpoint=False)).astype(np.int64)
+        self.timesteps = torch.from_numpy(origin[idx].astype(np.int64))
+
+    def _index(self, timestep):
+        return int((self.timesteps == int(timestep)).nonzero()[0])
+
+    def coefficients3(self, timestep):
+        """x_next = c_x x + c_e eps + c_n noise (c_n = 0 on the last step), fp64 on the host."""
+        i = self._index(timestep)
+        last = i == len(self.timesteps) - 1
+        t = int(timestep)
+        a_t = float(self.alphas_cumprod[t])
+        st = t * self.config.timestep_scaling
+        c_skip = 0.25 / (st * st + 0.25)
+        c_out = st / math.sqrt(st * st + 0.25)
+        d_x = c_out / math.sqrt(a_t) + c_skip                         # denoised = c_out (x - sqrt(1 - a_t) eps) / sqrt(a_t) + c_skip x
+        d_e = -c_out * math.sqrt(1.0 - a_t) / math.sqrt(a_t)
+        if last:
+            return d_x, d_e, 0.0
+        a_p = float(self.alphas_cumprod[int(self.timesteps[i + 1])])
+        return math.sqrt(a_p) * d_x, math.sqrt(a_p) * d_e, math.sqrt(1.0 - a_p)
+
+    def coefficients(self, timestep):
+        return self.coefficients3(timestep)[:2]
+
+    def _renoise(self, x, c_n, generator):
+        if c_n != 0.0:
+            gen = generator if generator is not None else self.generator
+            # [3P] randn_tensor: a CPU generator draws on the CPU and the noise is moved to the latents' device
+            where = gen.device if gen is not None else x.device
+            noise = torch.randn(x.shape, generator=gen, device=where, dtype=torch.float32).to(x.device)
+            ops.axpby(noise, x, 1.0, c_n, out=x)
+        return x
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=False, **_):
+        c_x, c_e, c_n = self.coefficients3(timestep)
+        prev = self._renoise(ops.axpby(model_output, sample, c_x, c_e), c_n, generator)
+        return SimpleNamespace(prev_sample=prev) if return_dict else (prev,)
+
+    def cfg_step(self, eps2, timestep, sample, guidance_scale, x_in_next2=None, out=None):
+        if x_in_next2 is not None:
+            raise NotImplementedError("LCM re-noises after the update: the duplicated next input cannot be written by the same kernel")
+        c_x, c_e, c_n = self.coefficients3(timestep)
+        return self._renoise(ops.cfg_ddim_step(eps2, sample, guidance_scale, c_x, c_e, x_out=out), c_n, None)
+
+    def inverse_coefficients(self, timestep, prev_timestep):
+        raise NotImplementedError("DDIM inversion runs on B200DDIMScheduler (pnp_pipeline.py:133)")

@@ -217,3 +217,43 @@ class EulerDiscreteSchedulerOracle:
         prev = sample + derivative * (self.sigmas[i + 1] - sigma)
         self._step_index = i + 1
         return (prev,)
+
+class LCMSchedulerOracle(_Base):
+    """[3P] diffusers ``LCMScheduler`` (0.26: ``set_timesteps`` by ``np.linspace`` over the reversed training-schedule points,
+    ``get_scalings_for_boundary_condition_discrete`` with sigma_data 0.5 and timestep_scaling 10, multistep re-noising),
+    epsilon prediction, no clipping / thresholding -- the scheduler of the reference's commented-out ``ipa_lcm`` mode
+    (sdxl_img2img_pipeline.py:91-104, serve.py:90).  Restated from the published algorithm: PARITY UNPINNED (no diffusers here,
+    and the reference never instantiates it)."""
+
+    def __init__(self, original_inference_steps=50, timestep_scaling=10.0, **kw):
+        super().__init__(**kw)
+        self.original_inference_steps, self.timestep_scaling, self.generator = original_inference_steps, timestep_scaling, None
+
+    def set_timesteps(self, num_inference_steps, device=None, original_inference_steps=None, strength=1.0):
+        self.num_inference_steps = num_inference_steps
+        orig = original_inference_steps or self.original_inference_steps
+        k = self._cfg["num_train_timesteps"] // orig
+        origin = np.asarray(list(range(1, int(orig * strength) + 1))) * k - 1
+        origin = origin[::-1].copy()
+        idx = np.floor(np.linspace(0, len(origin), num=num_inference_steps, endpoint=False)).astype(np.int64)
+        self.timesteps = torch.from_numpy(origin[idx]).to(dtype=torch.long)
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=False, **_):
+        i = int((self.timesteps == int(timestep)).nonzero()[0])
+        prev_t = self.timesteps[i + 1] if i + 1 < len(self.timesteps) else timestep
+        a_t = self.alphas_cumprod[int(timestep)]
+        a_p = self.alphas_cumprod[int(prev_t)] if int(prev_t) >= 0 else self.final_alpha_cumprod
+        scaled = int(timestep) * self.timestep_scaling
+        c_skip = 0.5 ** 2 / (scaled ** 2 + 0.5 ** 2)
+        c_out = scaled / (scaled ** 2 + 0.5 ** 2) ** 0.5
+        x0 = (sample - (1 - a_t) ** 0.5 * model_output) / a_t ** 0.5
+        denoised = c_out * x0 + c_skip * sample
+        if i != self.num_inference_steps - 1:
+            noise = torch.randn(model_output.shape, generator=generator if generator is not None else self.generator, dtype=denoised.dtype)
+            prev = a_p ** 0.5 * denoised + (1 - a_p) ** 0.5 * noise
+        else:
+            prev = denoised
+        return (prev,)
+
+
+LCMSchedulerOracle.add_noise = _ddim_add_noise

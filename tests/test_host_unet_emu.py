@@ -196,3 +196,33 @@ def test_nine_channel_inpainting_unet(emu):
     import pytest
     with pytest.raises(ValueError, match="9-channel"):
         B200Sampler(b, use_cuda_graph=False).generate(lat, ctx, added, num_inference_steps=2, init_latents=init, inpaint_mask=mask)
+
+def test_lcm_scheduler_tables_and_sampler(emu):
+    """B200LCMScheduler (the reference's 4-step ``ipa_lcm`` mode) against the restated [3P] LCMScheduler: the published
+    4-step timesteps of a 50-point training schedule, the three coefficients of every step against the oracle's step on random
+    tensors, and a free-running 4-step CFG trajectory through B200Sampler with identical noise draws."""
+    from instructany2pix_b200.scheduler import B200LCMScheduler
+    from oracle.schedulers import LCMSchedulerOracle
+    bs, os_ = B200LCMScheduler(), LCMSchedulerOracle()
+    for n in (1, 2, 4, 8):
+        bs.set_timesteps(n)
+        os_.set_timesteps(n)
+        assert bs.timesteps.tolist() == os_.timesteps.tolist()
+    bs.set_timesteps(4)
+    assert bs.timesteps.tolist() == [999, 759, 499, 259]
+    os_.set_timesteps(4)
+    g = torch.Generator().manual_seed(3)
+    x, e = torch.randn(1, 4, 8, 8, generator=g), torch.randn(1, 4, 8, 8, generator=g)
+    for t in bs.timesteps.tolist():
+        c_x, c_e, c_n = bs.coefficients3(t)
+        ref = os_.step(e, t, x, generator=torch.Generator().manual_seed(11))[0]
+        noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(11))
+        assert rel(c_x * x + c_e * e + c_n * noise, ref) < 1e-5
+    assert bs.coefficients3(259)[2] == 0.0                       # the last step is not re-noised
+    o, b = build_pair(True)
+    lat, ctx, added = make_inputs(TINY, B=1, L=8)
+    os2, bs2 = LCMSchedulerOracle(), B200LCMScheduler()
+    os2.generator, bs2.generator = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+    ref = osampler.generate(o, lat, ctx, added, num_inference_steps=4, guidance_scale=1.5, scheduler=os2)
+    out = B200Sampler(b, scheduler=bs2, use_cuda_graph=False).generate(lat, ctx, added, num_inference_steps=4, guidance_scale=1.5)
+    assert rel(out, ref) < 2e-2

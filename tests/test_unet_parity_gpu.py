@@ -315,6 +315,31 @@ def test_sampler_parity_euler():
     assert rel(sch.step(cu(eps), t, cu(x))[0].cpu(), osch.step(eps, t, x)[0]) < 1e-6
 
 
+def test_sampler_parity_lcm():
+    """LCMScheduler (the reference's 4-step ``ipa_lcm`` mode, sdxl_img2img_pipeline.py:91-104): consistency boundary
+    scalings + re-noising after every step but the last, on the fused CFG / update kernel + one axpby; CPU generators on both sides
+    give identical noise ([3P] randn_tensor semantics)."""
+    from instructany2pix_b200.scheduler import B200LCMScheduler
+    from oracle.schedulers import LCMSchedulerOracle
+    o, b = build_pair(True, device="cuda")
+    lat, ctx, added = make_inputs(TINY, B=2, L=16)
+    osch, bsch = LCMSchedulerOracle(), B200LCMScheduler()
+    osch.generator, bsch.generator = torch.Generator().manual_seed(9), torch.Generator().manual_seed(9)
+    tr_o = []
+    ref = osampler.generate(o, lat, ctx, added, num_inference_steps=4, guidance_scale=1.5, trace=tr_o, scheduler=osch)
+    s = B200Sampler(b, scheduler=bsch)
+    tr_b = []
+    s.generate(cu(lat), cu(ctx), cu(added), num_inference_steps=4, guidance_scale=1.5, trace=tr_b, teacher=[t["x"].cuda() for t in tr_o])
+    worst = max(rel(a["eps2"].cpu(), r["eps2"]) for a, r in zip(tr_b, tr_o))
+    print(f"LCM teacher-forced per-step eps rel-L2: worst {worst:.2e}")
+    assert worst < EPS_TOL
+    bsch.generator = torch.Generator().manual_seed(9)
+    free = s.generate(cu(lat), cu(ctx), cu(added), num_inference_steps=4, guidance_scale=1.5)
+    e = rel(free.cpu(), ref)
+    print(f"LCM free-running final latent rel-L2 (4 steps, identical noise): {e:.2e}")
+    assert e < 5e-2
+
+
 @pytest.mark.parametrize("sched", ["ddim", "euler"])
 @pytest.mark.parametrize("mode", ["img2img", "inpaint", "inpaint_full"])
 def test_img2img_and_inpainting_loops(sched, mode):
